@@ -1,0 +1,170 @@
+/*
+ * ORACLE — test infrastructure, NOT product code.
+ *
+ * A plain-C, single-threaded restatement of the reference's node-depth path, used
+ * only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs as the checker and the CPU baseline.  Nothing under pollen_b200/
+ * may include, link or call this file.
+ *
+ * Parity pinning: the Rust reference cannot be built here (no cargo/rustc, crates
+ * not vendored), so this restatement is pinned against (a) the reference's in-repo
+ * golden tables for the path (slow_odgi/README.md:147-175, flatgfa-sh/README.md:31-36)
+ * and (b) outputs of the reference's own Python implementation `slow_odgi depth`
+ * (slow_odgi/slow_odgi/depth.py:6-16) run in the build container on the reference's
+ * fixtures and on seeded random graphs; those outputs are committed under
+ * tests/golden/ together with the generating script (oracle/make_golden.py).
+ *
+ * Every function cites the reference lines it follows (paths relative to the
+ * reference checkout).
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* flatgfa/src/file.rs:9 */
+#define ORACLE_MAGIC 0xB1011054ull
+
+/* flatgfa/src/flatgfa.rs:201-203: Handle::segment() = word >> 1 (low bit = orientation). */
+static inline uint32_t handle_segment(uint32_t h) { return h >> 1; }
+
+/*
+ * flatgfa/src/ops/depth.rs:15-39  seg_depth_with_uniq.
+ * `spans` holds (start,end) u32 pairs, one per path, half-open ranges into `steps`
+ * (flatgfa/src/pool.rs:80-124, 341-347).  `depth`/`uniq` have n_segs entries
+ * (usize == u64 on the reference's only supported target).
+ * Returns 0, or -1 where the reference would panic on an out-of-bounds index
+ * (span outside the pool: pool.rs:341-347; segment id >= n_segs: depth.rs:29).
+ */
+int oracle_seg_depth_with_uniq(const uint32_t* steps, uint64_t n_steps, const uint32_t* spans,
+                               uint32_t n_paths, uint32_t n_segs, uint64_t* depth,
+                               uint64_t* uniq) {
+    /* depth.rs:17-18: vec![0; segs.len()] */
+    memset(depth, 0, (size_t)n_segs * sizeof(uint64_t));
+    memset(uniq, 0, (size_t)n_segs * sizeof(uint64_t));
+    /* depth.rs:23: BitVec::from_elem(segs.len(), false) */
+    size_t n_words = ((size_t)n_segs + 63) / 64;
+    uint64_t* seen = (uint64_t*)calloc(n_words ? n_words : 1, sizeof(uint64_t));
+    if (!seen) return -2;
+    for (uint32_t p = 0; p < n_paths; ++p) { /* depth.rs:25 */
+        uint32_t start = spans[2 * p], end = spans[2 * p + 1];
+        if (start > end || (uint64_t)end > n_steps) { free(seen); return -1; }
+        memset(seen, 0, n_words * sizeof(uint64_t)); /* depth.rs:26: seen.clear() */
+        for (uint32_t i = start; i < end; ++i) {     /* depth.rs:27 */
+            uint32_t seg = handle_segment(steps[i]); /* depth.rs:28 */
+            if (seg >= n_segs) { free(seen); return -1; }
+            depth[seg] += 1;                         /* depth.rs:29 */
+            uint64_t bit = 1ull << (seg & 63);
+            if (!(seen[seg >> 6] & bit)) {           /* depth.rs:30 */
+                uniq[seg] += 1;                      /* depth.rs:32 */
+                seen[seg >> 6] |= bit;               /* depth.rs:33 */
+            }
+        }
+    }
+    free(seen);
+    return 0;
+}
+
+/* flatgfa/src/ops/depth.rs:45-56  seg_depth (no unique depth). */
+int oracle_seg_depth(const uint32_t* steps, uint64_t n_steps, const uint32_t* spans,
+                     uint32_t n_paths, uint32_t n_segs, uint64_t* depth) {
+    memset(depth, 0, (size_t)n_segs * sizeof(uint64_t));
+    for (uint32_t p = 0; p < n_paths; ++p) {
+        uint32_t start = spans[2 * p], end = spans[2 * p + 1];
+        if (start > end || (uint64_t)end > n_steps) return -1;
+        for (uint32_t i = start; i < end; ++i) {
+            uint32_t seg = handle_segment(steps[i]);
+            if (seg >= n_segs) return -1;
+            depth[seg] += 1;
+        }
+    }
+    return 0;
+}
+
+/*
+ * flatgfa/src/file.rs:14-38 (Toc, Size), 163-213 (slice_prefix, read_toc, view).
+ * Locates the pools the depth path touches inside a .flatgfa image.  Pool order and
+ * element sizes: header u8, segs 24 B, paths 24 B, links 16 B, steps 4 B, ... ;
+ * each pool occupies capacity*sizeof(T) bytes of which the first len are valid.
+ */
+typedef struct {
+    uint64_t n_segs, n_paths, n_steps;
+    uint64_t segs_off, paths_off, steps_off; /* byte offsets into the image */
+} oracle_view_t;
+
+static uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+int oracle_view(const uint8_t* data, uint64_t len, oracle_view_t* out) {
+    if (len < 184) return -1;                     /* file.rs:170-171: Toc::ref_from_prefix */
+    if (rd64(data) != ORACLE_MAGIC) return -2;    /* file.rs:172-173 */
+    static const uint64_t elem[11] = {1, 24, 24, 16, 4, 1, 8, 4, 1, 1, 1};
+    uint64_t off = 184, offs[11], lens[11];
+    for (int i = 0; i < 11; ++i) {                /* file.rs:188-198 */
+        uint64_t l = rd64(data + 8 + 16 * i), cap = rd64(data + 16 + 16 * i);
+        if (cap < l) return -3;                   /* file.rs:165: capacity - len underflow */
+        offs[i] = off;
+        lens[i] = l;
+        if (off + cap * elem[i] < off || off + cap * elem[i] > len) return -4; /* file.rs:164 unwrap */
+        off += cap * elem[i];
+    }
+    out->n_segs = lens[1];  out->segs_off = offs[1];
+    out->n_paths = lens[2]; out->paths_off = offs[2];
+    out->n_steps = lens[4]; out->steps_off = offs[4];
+    return 0;
+}
+
+/*
+ * seg_depth_with_uniq over a .flatgfa image: extracts each Path's `steps` span
+ * (bytes 8..16 of the 24-byte packed record, flatgfa/src/flatgfa.rs:99-112) and the
+ * unaligned steps pool, then runs the loop above.
+ */
+int oracle_file_seg_depth_with_uniq(const uint8_t* data, uint64_t len, uint64_t* depth,
+                                    uint64_t* uniq) {
+    oracle_view_t v;
+    int rc = oracle_view(data, len, &v);
+    if (rc) return rc;
+    uint32_t* steps = (uint32_t*)malloc((size_t)(v.n_steps ? v.n_steps : 1) * 4);
+    uint32_t* spans = (uint32_t*)malloc((size_t)(v.n_paths ? v.n_paths : 1) * 8);
+    if (!steps || !spans) { free(steps); free(spans); return -5; }
+    memcpy(steps, data + v.steps_off, (size_t)v.n_steps * 4);
+    for (uint64_t p = 0; p < v.n_paths; ++p) {
+        spans[2 * p] = rd32(data + v.paths_off + 24 * p + 8);
+        spans[2 * p + 1] = rd32(data + v.paths_off + 24 * p + 12);
+    }
+    rc = oracle_seg_depth_with_uniq(steps, v.n_steps, spans, (uint32_t)v.n_paths,
+                                    (uint32_t)v.n_segs, depth, uniq);
+    free(steps);
+    free(spans);
+    return rc;
+}
+
+/*
+ * flatgfa/src/ops/depth.rs:61-82  SegDepth::emit: header line, then one row per
+ * segment in pool order with `seg.name as u32` (truncating cast, depth.rs:71).
+ * `names` are the usize names read at byte offset 24*i of the segs pool
+ * (flatgfa/src/flatgfa.rs:71-82).  Returns bytes written, or -1 if `cap` is too small.
+ */
+int64_t oracle_emit_seg_depth(const uint64_t* names, const uint64_t* depth, const uint64_t* uniq,
+                              uint32_t n_segs, char* buf, uint64_t cap) {
+    static const char hdr[] = "#node.id\tdepth\tdepth.uniq\n"; /* depth.rs:69 */
+    uint64_t n = 0;
+    if (cap < sizeof(hdr)) return -1;
+    memcpy(buf, hdr, sizeof(hdr) - 1);
+    n = sizeof(hdr) - 1;
+    for (uint32_t i = 0; i < n_segs; ++i) { /* depth.rs:70 */
+        if (cap - n < 64) return -1;
+        n += (uint64_t)snprintf(buf + n, cap - n, "%u\t%llu\t%llu\n", (uint32_t)names[i],
+                                (unsigned long long)depth[i], (unsigned long long)uniq[i]);
+    }
+    return (int64_t)n;
+}
+
+/* Segment names out of a .flatgfa image, for oracle_emit_seg_depth. */
+int oracle_file_seg_names(const uint8_t* data, uint64_t len, uint64_t* names) {
+    oracle_view_t v;
+    int rc = oracle_view(data, len, &v);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < v.n_segs; ++i) names[i] = rd64(data + v.segs_off + 24 * i);
+    return 0;
+}

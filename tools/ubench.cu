@@ -1,0 +1,211 @@
+// Kernel microbenchmark for the depth path (development tool; not the product bench).
+// Generates one synthetic config on the host, uploads it, times each kernel variant
+// with CUDA events and checks the full pipeline against the C oracle.
+//
+//   ubench <cfg: B|C|E|U> [reps] [verify 0/1]
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../pollen_b200/csrc/depth_kernels.cuh"
+
+extern "C" {
+int fgfa_synth_spans(uint32_t, uint64_t, uint32_t, uint64_t, uint32_t*, uint32_t*);
+int fgfa_synth_steps(int, uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint64_t,
+                     uint32_t*, int);
+int oracle_seg_depth_with_uniq(const uint32_t*, uint64_t, const uint32_t*, uint32_t, uint32_t,
+                               uint64_t*, uint64_t*);
+}
+
+#define CK(x)                                                                         \
+    do {                                                                              \
+        cudaError_t e_ = (x);                                                         \
+        if (e_ != cudaSuccess) {                                                      \
+            fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(1);                                                                  \
+        }                                                                             \
+    } while (0)
+
+using namespace fgfa;
+
+struct Cfg { const char* name; uint32_t n_segs, n_paths; uint64_t n_steps; int kind; uint32_t jitter; };
+
+int main(int argc, char** argv) {
+    std::string which = argc > 1 ? argv[1] : "B";
+    int reps = argc > 2 ? atoi(argv[2]) : 10;
+    int verify = argc > 3 ? atoi(argv[3]) : 1;
+    Cfg cfg;
+    if (which == "B") cfg = {"B", 1000000, 16, 20000000ull, 0, 0};
+    else if (which == "C") cfg = {"C", 5000000, 90, 400000000ull, 0, 20};
+    else if (which == "E") cfg = {"E", 5000000, 8, 400000000ull, 1, 0};
+    else if (which == "U") cfg = {"U", 5000000, 90, 400000000ull, 2, 20};
+    else if (which == "S") cfg = {"S", 5000, 7, 100003ull, 0, 30};
+    else { fprintf(stderr, "unknown cfg\n"); return 2; }
+
+    int n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads > 64) n_threads = 64;
+    std::vector<uint32_t> ss(cfg.n_paths), se(cfg.n_paths);
+    std::vector<uint32_t> steps(cfg.n_steps);
+    auto t0 = std::chrono::steady_clock::now();
+    fgfa_synth_spans(cfg.n_paths, cfg.n_steps, cfg.jitter, 0xB1011054ull, ss.data(), se.data());
+    fgfa_synth_steps(cfg.kind, cfg.n_segs, cfg.n_paths, ss.data(), se.data(), 0xB1011054ull,
+                     steps.data(), n_threads);
+    auto t1 = std::chrono::steady_clock::now();
+    printf("cfg %s: n_segs=%u n_paths=%u n_steps=%llu gen %.2fs (%d threads)\n", cfg.name,
+           cfg.n_segs, cfg.n_paths, (unsigned long long)cfg.n_steps,
+           std::chrono::duration<double>(t1 - t0).count(), n_threads);
+
+    // chunk table
+    std::vector<uint32_t> prefix(cfg.n_paths + 1, 0);
+    for (uint32_t p = 0; p < cfg.n_paths; ++p) {
+        uint64_t a = ss[p] & ~3u;
+        uint64_t n = se[p] > ss[p] ? (se[p] - a + kChunk - 1) / kChunk : 0;
+        prefix[p + 1] = prefix[p] + (uint32_t)n;
+    }
+    uint32_t n_chunks = prefix[cfg.n_paths];
+    uint32_t n_words = (cfg.n_segs + 31) / 32;
+    uint32_t wpr = (n_words + 31) & ~31u;
+
+    uint32_t *d_steps, *d_ss, *d_se, *d_prefix, *d_depth, *d_uniq, *d_bitmap, *d_err;
+    CK(cudaMalloc(&d_steps, cfg.n_steps * 4 + 16));
+    CK(cudaMalloc(&d_ss, cfg.n_paths * 4));
+    CK(cudaMalloc(&d_se, cfg.n_paths * 4));
+    CK(cudaMalloc(&d_prefix, (cfg.n_paths + 1) * 4));
+    CK(cudaMalloc(&d_depth, (size_t)cfg.n_segs * 4));
+    CK(cudaMalloc(&d_uniq, (size_t)cfg.n_segs * 4));
+    CK(cudaMalloc(&d_bitmap, (size_t)cfg.n_paths * wpr * 4));
+    CK(cudaMalloc(&d_err, 4));
+    CK(cudaMemcpy(d_steps, steps.data(), cfg.n_steps * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ss, ss.data(), cfg.n_paths * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_se, se.data(), cfg.n_paths * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_prefix, prefix.data(), (cfg.n_paths + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_bitmap, 0, (size_t)cfg.n_paths * wpr * 4));
+    CK(cudaMemset(d_err, 0, 4));
+
+    StreamParams P{};
+    P.steps = d_steps; P.n_steps = cfg.n_steps; P.span_start = d_ss; P.span_end = d_se;
+    P.chunk_prefix = d_prefix; P.path_lo = 0; P.path_hi = cfg.n_paths; P.n_segs = cfg.n_segs;
+    P.words_per_row = wpr; P.depth = d_depth; P.bitmap = d_bitmap; P.err = d_err;
+    PopcountParams Q{};
+    Q.bitmap = d_bitmap; Q.n_rows = cfg.n_paths; Q.words_per_row = wpr; Q.n_words = n_words;
+    Q.n_segs = cfg.n_segs; Q.uniq = d_uniq; Q.accumulate = 0;
+
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    int sms = prop.multiProcessorCount;
+    printf("device %s, %d SMs, chunks=%u, bitmap %.1f MB\n", prop.name, sms, n_chunks,
+           (double)cfg.n_paths * wpr * 4 / 1e6);
+
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const double alg_bytes = 4.0 * cfg.n_steps + 8.0 * cfg.n_paths + 8.0 * cfg.n_segs;
+
+    auto time_it = [&](const char* name, auto&& launch, bool clear_bitmap) {
+        float best = 1e30f, sum = 0;
+        for (int r = 0; r < reps + 2; ++r) {
+            CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
+            if (clear_bitmap) CK(cudaMemsetAsync(d_bitmap, 0, (size_t)cfg.n_paths * wpr * 4));
+            CK(cudaEventRecord(e0));
+            launch();
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (r >= 2) { best = std::min(best, ms); sum += ms; }
+        }
+        float avg = sum / reps;
+        printf("%-34s best %8.3f ms  avg %8.3f ms  %8.1f Gstep/s  alg %7.1f GB/s (%.1f%% of 6540)\n",
+               name, best, avg, cfg.n_steps / (avg * 1e6), alg_bytes / (avg * 1e6),
+               100.0 * alg_bytes / (avg * 1e6) / 6540.2);
+    };
+
+    for (int bps : {2, 4, 8}) {
+        int grid = sms * bps;
+        char nm[96];
+        snprintf(nm, sizeof nm, "read-only lane-order g=%dxSM", bps);
+        time_it(nm, [&] { k_step_stream_direct<kModeReadOnly, 1><<<grid, kThreads>>>(P); }, false);
+        snprintf(nm, sizeof nm, "read-only v4 g=%dxSM", bps);
+        time_it(nm, [&] { k_step_stream_direct<kModeReadOnly, 0><<<grid, kThreads>>>(P); }, false);
+    }
+    for (int bps : {4, 8}) {
+        int grid = sms * bps;
+        char nm[96];
+        snprintf(nm, sizeof nm, "depth-only lane-order g=%dxSM", bps);
+        time_it(nm, [&] { k_step_stream_direct<kModeDepthOnly, 1><<<grid, kThreads>>>(P); }, false);
+        snprintf(nm, sizeof nm, "depth-only v4 g=%dxSM", bps);
+        time_it(nm, [&] { k_step_stream_direct<kModeDepthOnly, 0><<<grid, kThreads>>>(P); }, false);
+        snprintf(nm, sizeof nm, "seen-only lane-order g=%dxSM", bps);
+        time_it(nm, [&] { k_step_stream_direct<kModeSeenOnly, 1><<<grid, kThreads>>>(P); }, true);
+        snprintf(nm, sizeof nm, "seen-only v4 g=%dxSM", bps);
+        time_it(nm, [&] { k_step_stream_direct<kModeSeenOnly, 0><<<grid, kThreads>>>(P); }, true);
+        snprintf(nm, sizeof nm, "depth+seen lane-order g=%dxSM", bps);
+        time_it(nm, [&] { k_step_stream_direct<kModeDepthAndSeen, 1><<<grid, kThreads>>>(P); }, true);
+        snprintf(nm, sizeof nm, "depth+seen v4 g=%dxSM", bps);
+        time_it(nm, [&] { k_step_stream_direct<kModeDepthAndSeen, 0><<<grid, kThreads>>>(P); }, true);
+    }
+    {
+        int pgrid = (n_words + 255) / 256;
+        // populate bitmap once, then time popcount (it clears as it goes, so refill each rep)
+        float best = 1e30f;
+        for (int r = 0; r < reps; ++r) {
+            k_step_stream_direct<kModeSeenOnly, 1><<<sms * 8, kThreads>>>(P);
+            CK(cudaEventRecord(e0));
+            k_uniq_popcount<<<pgrid, 256>>>(Q);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+        }
+        printf("%-34s best %8.3f ms\n", "uniq popcount", best);
+        // full pipeline: memset + A + B
+        float sum = 0; best = 1e30f;
+        for (int r = 0; r < reps + 2; ++r) {
+            CK(cudaEventRecord(e0));
+            CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
+            k_step_stream_direct<kModeDepthAndSeen, 1><<<sms * 8, kThreads>>>(P);
+            k_uniq_popcount<<<pgrid, 256>>>(Q);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (r >= 2) { best = std::min(best, ms); sum += ms; }
+        }
+        float avg = sum / reps;
+        printf("%-34s best %8.3f ms  avg %8.3f ms  %8.1f Gstep/s  alg %7.1f GB/s (%.1f%% of 6540)\n",
+               "PIPELINE memset+A+B", best, avg, cfg.n_steps / (avg * 1e6), alg_bytes / (avg * 1e6),
+               100.0 * alg_bytes / (avg * 1e6) / 6540.2);
+    }
+    CK(cudaDeviceSynchronize());
+    uint32_t err;
+    CK(cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));
+    printf("err flag = %u\n", err);
+
+    if (verify) {
+        std::vector<uint32_t> g_depth(cfg.n_segs), g_uniq(cfg.n_segs);
+        CK(cudaMemcpy(g_depth.data(), d_depth, (size_t)cfg.n_segs * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_uniq.data(), d_uniq, (size_t)cfg.n_segs * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> spans(2 * cfg.n_paths);
+        for (uint32_t p = 0; p < cfg.n_paths; ++p) { spans[2 * p] = ss[p]; spans[2 * p + 1] = se[p]; }
+        std::vector<uint64_t> o_depth(cfg.n_segs), o_uniq(cfg.n_segs);
+        auto c0 = std::chrono::steady_clock::now();
+        int rc = oracle_seg_depth_with_uniq(steps.data(), cfg.n_steps, spans.data(), cfg.n_paths,
+                                            cfg.n_segs, o_depth.data(), o_uniq.data());
+        auto c1 = std::chrono::steady_clock::now();
+        double cs = std::chrono::duration<double>(c1 - c0).count();
+        uint64_t bad = 0, sum_d = 0, sum_u = 0;
+        for (uint32_t i = 0; i < cfg.n_segs; ++i) {
+            bad += (g_depth[i] != o_depth[i]) + (g_uniq[i] != o_uniq[i]);
+            sum_d += o_depth[i]; sum_u += o_uniq[i];
+        }
+        printf("oracle rc=%d  %.3f s (%.1f Mstep/s, 1 core)  sum_depth=%llu sum_uniq=%llu  mismatches=%llu %s\n",
+               rc, cs, cfg.n_steps / cs / 1e6, (unsigned long long)sum_d, (unsigned long long)sum_u,
+               (unsigned long long)bad, bad ? "FAIL" : "PARITY OK");
+    }
+    return 0;
+}
