@@ -12,7 +12,7 @@
 #include <thread>
 #include <vector>
 
-#include "../pollen_b200/csrc/depth_kernels.cuh"
+#include "experimental_kernels.cuh"
 
 extern "C" {
 int fgfa_synth_spans(uint32_t, uint64_t, uint32_t, uint64_t, uint32_t*, uint32_t*);
@@ -93,7 +93,7 @@ int main(int argc, char** argv) {
     P.words_per_row = wpr; P.depth = d_depth; P.bitmap = d_bitmap; P.err = d_err;
     PopcountParams Q{};
     Q.bitmap = d_bitmap; Q.n_rows = cfg.n_paths; Q.words_per_row = wpr; Q.n_words = n_words;
-    Q.n_segs = cfg.n_segs; Q.uniq = d_uniq; Q.accumulate = 0;
+    Q.n_segs = cfg.n_segs; Q.uniq = d_uniq; Q.depth = nullptr; Q.accumulate = 0;
 
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -151,13 +151,13 @@ int main(int argc, char** argv) {
         time_it(nm, [&] { k_step_stream_direct<kModeDepthAndSeen, 0><<<grid, kThreads>>>(P); }, true);
     }
     {
-        int pgrid = (n_words + 255) / 256;
+        int pgrid = (n_words + kPopThreads - 1) / kPopThreads;
         // populate bitmap once, then time popcount (it clears as it goes, so refill each rep)
         float best = 1e30f;
         for (int r = 0; r < reps; ++r) {
             k_step_stream_direct<kModeSeenOnly, 1><<<sms * 8, kThreads>>>(P);
             CK(cudaEventRecord(e0));
-            k_uniq_popcount<<<pgrid, 256>>>(Q);
+            k_uniq_popcount<<<pgrid, kPopThreads>>>(Q);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -170,7 +170,7 @@ int main(int argc, char** argv) {
             CK(cudaEventRecord(e0));
             CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
             k_step_stream_direct<kModeDepthAndSeen, 1><<<sms * 8, kThreads>>>(P);
-            k_uniq_popcount<<<pgrid, 256>>>(Q);
+            k_uniq_popcount<<<pgrid, kPopThreads>>>(Q);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -180,6 +180,56 @@ int main(int argc, char** argv) {
         printf("%-34s best %8.3f ms  avg %8.3f ms  %8.1f Gstep/s  alg %7.1f GB/s (%.1f%% of 6540)\n",
                "PIPELINE memset+A+B", best, avg, cfg.n_steps / (avg * 1e6), alg_bytes / (avg * 1e6),
                100.0 * alg_bytes / (avg * 1e6) / 6540.2);
+    }
+    {
+        int pgrid = (n_words + kPopThreads - 1) / kPopThreads;
+        PopcountParams Q2 = Q; Q2.depth = d_depth;
+        auto run_ft = [&](int bps) {
+            int grid = sms * bps;
+            if (bps == 2) k_step_stream_first_touch<2><<<grid, kThreads>>>(P);
+            else if (bps == 3) k_step_stream_first_touch<3><<<grid, kThreads>>>(P);
+            else if (bps == 4) k_step_stream_first_touch<4><<<grid, kThreads>>>(P);
+            else if (bps == 6) k_step_stream_first_touch<6><<<grid, kThreads>>>(P);
+            else k_step_stream_first_touch<8><<<grid, kThreads>>>(P);
+        };
+        for (int bps : {2, 3, 4, 6, 8}) {
+            char nm[96];
+            snprintf(nm, sizeof nm, "first-touch A only g=%dxSM", bps);
+            time_it(nm, [&] { run_ft(bps); }, true);
+        }
+        time_it("depth-only half-lanes(seg even) g=8xSM", [&] { k_step_stream_direct<kModeDepthHalfLanes, 1><<<sms * 8, kThreads>>>(P); }, false);
+        time_it("depth-only pairs(+2 even tid) g=8xSM", [&] { k_step_stream_direct<kModeDepthPairs, 1><<<sms * 8, kThreads>>>(P); }, false);
+        time_it("merged depth+seen g=4xSM", [&] { k_step_stream_merged<4, true><<<sms * 4, kThreads>>>(P); }, true);
+        time_it("merged depth+seen g=6xSM", [&] { k_step_stream_merged<6, true><<<sms * 6, kThreads>>>(P); }, true);
+        time_it("merged depth+seen g=8xSM", [&] { k_step_stream_merged<8, true><<<sms * 8, kThreads>>>(P); }, true);
+        time_it("merged depth-only g=8xSM", [&] { k_step_stream_merged<8, false><<<sms * 8, kThreads>>>(P); }, true);
+        time_it("warp-agg A only g=4xSM", [&] { k_step_stream_warp_agg<4><<<sms * 4, kThreads>>>(P); }, true);
+        time_it("warp-agg A only g=6xSM", [&] { k_step_stream_warp_agg<6><<<sms * 6, kThreads>>>(P); }, true);
+        time_it("warp-agg A only g=8xSM", [&] { k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); }, true);
+        time_it("FT exp1 (no pass3) g=4xSM", [&] { k_step_stream_first_touch<4, 1><<<sms * 4, kThreads>>>(P); }, true);
+        time_it("FT exp2 (RED.OR, no pass3) g=4xSM", [&] { k_step_stream_first_touch<4, 2><<<sms * 4, kThreads>>>(P); }, true);
+        time_it("FT exp3 (no atomics) g=4xSM", [&] { k_step_stream_first_touch<4, 3><<<sms * 4, kThreads>>>(P); }, true);
+        const bool use_wagg = getenv("UBENCH_WAGG") != nullptr;
+        const bool use_merged = getenv("UBENCH_MERGED") != nullptr;
+        if (use_merged) Q2.depth = nullptr;
+        for (int bps : {3, 4, 6, 8}) {
+            float sum = 0, best = 1e30f;
+            for (int r = 0; r < reps + 2; ++r) {
+                CK(cudaEventRecord(e0));
+                CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
+                if (use_merged) k_step_stream_merged<8, true><<<sms * 8, kThreads>>>(P); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
+                k_uniq_popcount<<<pgrid, kPopThreads>>>(Q2);
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                CK(cudaGetLastError());
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (r >= 2) { best = std::min(best, ms); sum += ms; }
+            }
+            float avg = sum / reps;
+            printf("FT PIPELINE memset+A+B g=%dxSM      best %8.3f ms  avg %8.3f ms  %8.1f Gstep/s  alg %7.1f GB/s (%.1f%% of 6540)\n",
+                   bps, best, avg, cfg.n_steps / (avg * 1e6), alg_bytes / (avg * 1e6),
+                   100.0 * alg_bytes / (avg * 1e6) / 6540.2);
+        }
     }
     CK(cudaDeviceSynchronize());
     uint32_t err;
