@@ -1,0 +1,50 @@
+# Build of the B200-native node-depth library, CLI, oracle and tools.
+# Everything CUDA is compiled for sm_100a only.
+NVCC      ?= nvcc
+CXX       ?= g++
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function
+CXXFLAGS  := -O3 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include
+CSRC      := pollen_b200/csrc
+LIBDIR    := pollen_b200/lib
+OBJDIR    := build/obj
+
+LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/ops_depth.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/capi.o
+
+all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools
+
+$(OBJDIR)/depth_device.o: $(CSRC)/depth_device.cu $(CSRC)/depth_kernels.cuh include/fgfa_depth.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.hpp) include/fgfa_depth.h include/flatgfa.h
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIBDIR)/libflatgfa.so: $(LIB_OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS) -cudart static -lpthread
+
+$(LIBDIR)/libfgfa_synth.so: $(CSRC)/synth.cpp
+	@mkdir -p $(LIBDIR)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $< -lpthread
+
+bin/fgfa: $(CSRC)/fgfa_main.cpp $(LIBDIR)/libflatgfa.so
+	@mkdir -p bin
+	$(CXX) $(CXXFLAGS) -o $@ $< -L$(LIBDIR) -lflatgfa -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+
+oracle:
+	$(MAKE) -C oracle
+
+tools: build/ubench
+build/ubench: tools/ubench.cu tools/experimental_kernels.cuh $(CSRC)/depth_kernels.cuh $(CSRC)/synth.cpp oracle/depth_oracle.c
+	@mkdir -p build
+	$(CC) -O3 -c oracle/depth_oracle.c -o build/depth_oracle.o
+	$(CXX) -O3 -std=c++17 -c $(CSRC)/synth.cpp -o build/synth.o
+	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench.cu build/depth_oracle.o build/synth.o -o $@
+
+clean:
+	rm -rf build bin $(LIBDIR)/*.so oracle/*.so
+
+.PHONY: all oracle tools clean

@@ -1,0 +1,131 @@
+/*
+ * fgfa_depth.h -- thin C ABI of the B200 node-depth engine.
+ *
+ * This is the boundary a Rust `extern "C"` block in the reference's `flatgfa` crate
+ * would bind to replace the body of
+ *     flatgfa/src/ops/depth.rs:15-39   pub fn seg_depth_with_uniq(gfa) -> (Vec<usize>, Vec<usize>)
+ *     flatgfa/src/ops/depth.rs:45-56   pub fn seg_depth(gfa) -> Vec<usize>
+ * (callers: flatgfa/src/cli/cmds.rs:239, flatgfa-sh/src/eval/instr.rs:30,
+ * flatgfa/src/ops/window_depth.rs:177).  Plain pointers and sizes only; no C++ or
+ * torch types.  The reference has no such export today (flatgfa-c/src/lib.rs exposes
+ * only per-step accessors), see INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Data conventions (all little-endian, as in the .flatgfa format):
+ *   steps       u32 Handle words, segment index << 1 | orientation  (flatgfa.rs:186-198)
+ *   span_start/ per-path half-open range [start,end) into `steps`   (flatgfa.rs:99-112,
+ *   span_end    pool.rs:80-124); arbitrary order/overlap is honoured
+ *   depth/uniq  one counter per segment, indexed by segment pool index (depth.rs:17-18)
+ *
+ * Errors: every function returns FGFA_OK (0) or a negative code; nothing aborts or
+ * throws across this boundary.  Where the reference would panic (span outside the
+ * pool, segment id >= n_segs: pool.rs:341-347, depth.rs:29) the call fails with
+ * FGFA_ERR_SPAN_OOB / FGFA_ERR_SEG_OOB and the outputs are unspecified.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point returns
+ * FGFA_ERR_NO_DEVICE.
+ */
+#ifndef FGFA_DEPTH_H
+#define FGFA_DEPTH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    FGFA_OK = 0,
+    FGFA_ERR_INVALID_ARG = -1, /* null pointer, misaligned device pointer, ... */
+    FGFA_ERR_BAD_MAGIC = -2,   /* .flatgfa image: magic != 0xB1011054 (file.rs:9,172-173) */
+    FGFA_ERR_TRUNCATED = -3,   /* .flatgfa image shorter than its table of contents says */
+    FGFA_ERR_SPAN_OOB = -4,    /* a path's steps span lies outside the steps pool */
+    FGFA_ERR_SEG_OOB = -5,     /* a step names a segment index >= n_segs */
+    FGFA_ERR_CUDA = -6,        /* CUDA runtime failure; see fgfa_last_error() */
+    FGFA_ERR_NOMEM = -7,
+    FGFA_ERR_NO_DEVICE = -8,   /* no usable CUDA device: the product has no CPU path */
+    FGFA_ERR_TOO_LARGE = -9    /* counts do not fit the format's u32 ids (pool.rs:9-11) */
+};
+
+/* Static description of an error code. */
+const char* fgfa_strerror(int code);
+/* Detail of the last failure on the calling thread (CUDA error string etc.). */
+const char* fgfa_last_error(void);
+
+/* ---- device-resident API -------------------------------------------------------- */
+
+/* A plan owns everything that depends only on the graph's shape: the chunk table
+ * derived from the path spans, the per-path `seen` bitmap scratch (the GPU form of
+ * depth.rs:23's BitVec), launch geometry.  Create once, run many times; runs enqueue
+ * only asynchronous work on the caller's stream (CUDA-graph capturable). */
+typedef struct fgfa_depth_plan fgfa_depth_plan_t;
+
+/* h_span_start/h_span_end: HOST arrays of n_paths entries.  bitmap_budget_bytes caps
+ * the seen-bitmap scratch (paths are processed in batches that fit); 0 = default. */
+int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start,
+                           const uint32_t* h_span_end, uint32_t n_paths, uint32_t n_segs,
+                           uint64_t n_steps, size_t bitmap_budget_bytes);
+void fgfa_depth_plan_destroy(fgfa_depth_plan_t* plan);
+
+/* seg_depth_with_uniq on device buffers.  d_steps: n_steps Handle words (4-byte
+ * aligned; 16-byte aligned for full speed).  d_depth, d_uniq: n_segs u32 each, fully
+ * overwritten (zero-initialisation is part of the run, as `vec![0; n]` is part of the
+ * reference's, depth.rs:17-18).  d_uniq may be NULL: then this is seg_depth
+ * (depth.rs:45-56).  u32 counters cannot overflow: a depth is at most n_steps < 2^32. */
+int fgfa_depth_plan_run(fgfa_depth_plan_t* plan, const uint32_t* d_steps, uint32_t* d_depth,
+                        uint32_t* d_uniq, void* cuda_stream);
+
+/* Same, restricted to paths [path_lo, path_hi) and WITHOUT zeroing d_depth first or
+ * running the uniq reduction: lets a host pipeline overlap uploads with compute.
+ * Finish with fgfa_depth_plan_finish().  Paths must be fed in increasing order. */
+int fgfa_depth_plan_begin(fgfa_depth_plan_t* plan, uint32_t* d_depth, void* cuda_stream);
+int fgfa_depth_plan_feed(fgfa_depth_plan_t* plan, const uint32_t* d_steps, uint32_t path_lo,
+                         uint32_t path_hi, uint32_t* d_depth, uint32_t* d_uniq, void* cuda_stream);
+int fgfa_depth_plan_finish(fgfa_depth_plan_t* plan, uint32_t* d_uniq, void* cuda_stream);
+
+/* Synchronise the stream and report the sticky device status of the runs since the
+ * last call: FGFA_OK, FGFA_ERR_SEG_OOB or FGFA_ERR_CUDA. */
+int fgfa_depth_plan_status(fgfa_depth_plan_t* plan, void* cuda_stream);
+
+/* Measurement hook: the next fgfa_depth_plan_run/feed records `before` immediately
+ * before and `after` immediately after its step-stream kernel launches (CUDA events
+ * owned by the caller, timing enabled).  Pass NULLs to clear.  One-shot: cleared after
+ * the run that used it. */
+int fgfa_depth_plan_set_probe(fgfa_depth_plan_t* plan, void* cuda_event_before, void* cuda_event_after);
+
+/* Kernel launches one fgfa_depth_plan_run enqueues (for launch accounting). */
+uint32_t fgfa_depth_plan_launches(const fgfa_depth_plan_t* plan, int with_uniq);
+/* Bytes of device scratch the plan holds. */
+size_t fgfa_depth_plan_scratch_bytes(const fgfa_depth_plan_t* plan);
+
+/* One-shot form with the span table on the device too (creates and destroys a plan;
+ * synchronises). */
+int fgfa_depth_device(const uint32_t* d_steps, uint64_t n_steps, const uint32_t* d_span_start,
+                      const uint32_t* d_span_end, uint32_t n_paths, uint32_t n_segs,
+                      uint32_t* d_depth, uint32_t* d_uniq, void* cuda_stream);
+
+/* ---- host-buffer API (uploads, runs, downloads; synchronous) -------------------- */
+
+/* seg_depth_with_uniq over host arrays.  depth_out/uniq_out: n_segs u64 (= Rust usize)
+ * each; uniq_out may be NULL (seg_depth).  h_steps may be pageable or pinned. */
+int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
+                                   const uint32_t* h_span_start, const uint32_t* h_span_end,
+                                   uint32_t n_paths, uint32_t n_segs, uint64_t* depth_out,
+                                   uint64_t* uniq_out);
+
+/* seg_depth_with_uniq / seg_depth over a .flatgfa image in host memory (e.g. the mmap
+ * the reference's `file::view` takes, file.rs:185-213).  Outputs: n_segs u64 each,
+ * where n_segs is what fgfa_flatgfa_counts() reports. */
+int fgfa_flatgfa_counts(const void* flatgfa_bytes, size_t len, uint64_t* n_segs,
+                        uint64_t* n_paths, uint64_t* n_steps);
+int fgfa_seg_depth_with_uniq(const void* flatgfa_bytes, size_t len, uint64_t* depth_out,
+                             uint64_t* uniq_out);
+int fgfa_seg_depth(const void* flatgfa_bytes, size_t len, uint64_t* depth_out);
+
+/* Number of CUDA devices visible (0 if none / no driver). */
+int fgfa_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGFA_DEPTH_H */

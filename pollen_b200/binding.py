@@ -1,0 +1,302 @@
+"""ctypes binding of libflatgfa.so and the Python mirror of the depth op.
+
+Names follow the reference: ``seg_depth_with_uniq`` / ``seg_depth`` / ``SegDepth``
+(flatgfa/src/ops/depth.rs:15,45,61) and the flatgfa-c accessors
+(flatgfa-c/src/lib.rs:62-172).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libflatgfa.so")
+_lib = None
+
+FGFA_OK = 0
+FGFA_ERR_INVALID_ARG = -1
+FGFA_ERR_BAD_MAGIC = -2
+FGFA_ERR_TRUNCATED = -3
+FGFA_ERR_SPAN_OOB = -4
+FGFA_ERR_SEG_OOB = -5
+FGFA_ERR_CUDA = -6
+FGFA_ERR_NOMEM = -7
+FGFA_ERR_NO_DEVICE = -8
+FGFA_ERR_TOO_LARGE = -9
+
+
+class DepthError(RuntimeError):
+    """A failed call into the depth engine; ``code`` is the FGFA_ERR_* value."""
+
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        msg = lib().fgfa_strerror(code).decode()
+        if detail:
+            msg += ": " + detail
+        super().__init__(msg)
+
+
+class _String(C.Structure):  # flatgfa_string_t (flatgfa-c/src/lib.rs:36-40)
+    _fields_ = [("data", C.POINTER(C.c_uint8)), ("len", C.c_int)]
+
+
+class _Handle(C.Structure):  # flatgfa_handle_t (flatgfa-c/src/lib.rs:140-144)
+    _fields_ = [("segment_id", C.c_uint32), ("is_forward", C.c_bool)]
+
+
+EXPORTS = {
+    # include/flatgfa.h
+    "flatgfa_parse": (C.c_void_p, [C.c_char_p]),
+    "flatgfa_free": (None, [C.c_void_p]),
+    "flatgfa_get_segment_count": (C.c_uint32, [C.c_void_p]),
+    "flatgfa_get_seq": (_String, [C.c_void_p, C.c_uint32]),
+    "flatgfa_path_count": (C.c_uint32, [C.c_void_p]),
+    "flatgfa_get_path_name": (_String, [C.c_void_p, C.c_uint32]),
+    "flatgfa_get_path_step_count": (C.c_uint32, [C.c_void_p, C.c_uint32]),
+    "flatgfa_get_step": (C.c_bool, [C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(_Handle)]),
+    "flatgfa_load": (C.c_void_p, [C.c_char_p]),
+    "flatgfa_seg_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "flatgfa_format_seg_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "flatgfa_dump": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "flatgfa_last_error": (C.c_char_p, []),
+    # include/fgfa_depth.h
+    "fgfa_strerror": (C.c_char_p, [C.c_int]),
+    "fgfa_last_error": (C.c_char_p, []),
+    "fgfa_device_count": (C.c_int, []),
+    "fgfa_depth_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_size_t]),
+    "fgfa_depth_plan_destroy": (None, [C.c_void_p]),
+    "fgfa_depth_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_set_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_launches": (C.c_uint32, [C.c_void_p, C.c_int]),
+    "fgfa_depth_plan_scratch_bytes": (C.c_size_t, [C.c_void_p]),
+    "fgfa_depth_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_seg_depth_with_uniq_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fgfa_flatgfa_counts": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fgfa_seg_depth_with_uniq": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "fgfa_seg_depth": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libflatgfa.so (built in-tree by ``make`` / ``__graft_entry__.build()``).
+
+    Fails loudly if the library is missing: the product path has no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(
+                f"{_LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()); "
+                "pollen_b200 has no CPU fallback"
+            )
+        handle = C.CDLL(_LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(handle, name)  # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def device_count() -> int:
+    return int(lib().fgfa_device_count())
+
+
+def _check(rc: int) -> None:
+    if rc != FGFA_OK:
+        raise DepthError(rc, lib().fgfa_last_error().decode())
+
+
+def _u32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def seg_depth_with_uniq_steps(steps, span_start, span_end, n_segs: int, want_uniq: bool = True):
+    """seg_depth_with_uniq (depth.rs:15-39) over raw host arrays: ``steps`` are Handle
+    words, ``span_start/span_end`` each path's half-open range.  Returns (depth, uniq)
+    as uint64 arrays (uniq is None if ``want_uniq`` is false)."""
+    steps, span_start, span_end = _u32(steps), _u32(span_start), _u32(span_end)
+    depth = np.empty(n_segs, dtype=np.uint64)
+    uniq = np.empty(n_segs, dtype=np.uint64) if want_uniq else None
+    _check(
+        lib().fgfa_seg_depth_with_uniq_steps(
+            steps.ctypes.data, steps.size, span_start.ctypes.data, span_end.ctypes.data,
+            span_start.size, n_segs, depth.ctypes.data, uniq.ctypes.data if want_uniq else None,
+        )
+    )
+    return depth, uniq
+
+
+def seg_depth_steps(steps, span_start, span_end, n_segs: int) -> np.ndarray:
+    """seg_depth (depth.rs:45-56) over raw host arrays."""
+    return seg_depth_with_uniq_steps(steps, span_start, span_end, n_segs, want_uniq=False)[0]
+
+
+class FlatGFA:
+    """A graph handle (``flatgfa_t``): parsed from GFA text or mapped from a .flatgfa file."""
+
+    def __init__(self, handle: int):
+        if not handle:
+            raise DepthError(FGFA_ERR_INVALID_ARG, lib().flatgfa_last_error().decode())
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def parse(cls, gfa_path: str) -> "FlatGFA":  # flatgfa_parse, lib.rs:62-68
+        return cls(lib().flatgfa_parse(os.fsencode(gfa_path)))
+
+    @classmethod
+    def load(cls, flatgfa_path: str) -> "FlatGFA":  # memfile::map_file + file::view
+        return cls(lib().flatgfa_load(os.fsencode(flatgfa_path)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().flatgfa_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def segment_count(self) -> int:
+        return int(lib().flatgfa_get_segment_count(self._h))
+
+    @property
+    def path_count(self) -> int:
+        return int(lib().flatgfa_path_count(self._h))
+
+    def seq(self, segment_id: int) -> Optional[bytes]:
+        s = lib().flatgfa_get_seq(self._h, segment_id)
+        return C.string_at(s.data, s.len) if s.data else None
+
+    def path_name(self, path_index: int) -> Optional[bytes]:
+        s = lib().flatgfa_get_path_name(self._h, path_index)
+        return C.string_at(s.data, s.len) if s.data else None
+
+    def path_step_count(self, path_index: int) -> int:
+        return int(lib().flatgfa_get_path_step_count(self._h, path_index))
+
+    def step(self, path_index: int, step_index: int) -> Optional[Tuple[int, bool]]:
+        out = _Handle()
+        ok = lib().flatgfa_get_step(self._h, path_index, step_index, C.byref(out))
+        return (int(out.segment_id), bool(out.is_forward)) if ok else None
+
+    def dump(self, flatgfa_path: str) -> None:
+        _check(lib().flatgfa_dump(self._h, os.fsencode(flatgfa_path)))
+
+    def seg_depth_with_uniq(self) -> Tuple[np.ndarray, np.ndarray]:
+        n = self.segment_count
+        depth = np.empty(n, dtype=np.uint64)
+        uniq = np.empty(n, dtype=np.uint64)
+        _check(lib().flatgfa_seg_depth(self._h, depth.ctypes.data, uniq.ctypes.data))
+        return depth, uniq
+
+    def seg_depth(self) -> np.ndarray:
+        depth = np.empty(self.segment_count, dtype=np.uint64)
+        _check(lib().flatgfa_seg_depth(self._h, depth.ctypes.data, None))
+        return depth
+
+    def format_seg_depth(self, depth: np.ndarray, uniq: np.ndarray) -> bytes:
+        depth = np.ascontiguousarray(depth, dtype=np.uint64)
+        uniq = np.ascontiguousarray(uniq, dtype=np.uint64)
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().flatgfa_format_seg_depth(self._h, depth.ctypes.data, uniq.ctypes.data, C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            C.CDLL(None).free(out)
+
+
+def seg_depth_with_uniq(gfa: FlatGFA) -> Tuple[np.ndarray, np.ndarray]:
+    """``ops::depth::seg_depth_with_uniq`` (flatgfa/src/ops/depth.rs:15)."""
+    return gfa.seg_depth_with_uniq()
+
+
+def seg_depth(gfa: FlatGFA) -> np.ndarray:
+    """``ops::depth::seg_depth`` (flatgfa/src/ops/depth.rs:45)."""
+    return gfa.seg_depth()
+
+
+class SegDepth:
+    """``ops::depth::SegDepth`` (flatgfa/src/ops/depth.rs:61-82): the printable table."""
+
+    def __init__(self, gfa: FlatGFA, depths: np.ndarray, uniq_depths: np.ndarray):
+        self.gfa, self.depths, self.uniq_depths = gfa, depths, uniq_depths
+
+    def emit(self) -> bytes:
+        return self.gfa.format_seg_depth(self.depths, self.uniq_depths)
+
+
+class DepthPlan:
+    """Device-resident form: a plan (chunk table + seen-bitmap scratch) run on device
+    buffers.  Buffers are torch CUDA tensors (uint32 viewed as int32 is fine: only
+    ``data_ptr()`` is used); torch is plumbing for memory and streams here."""
+
+    def __init__(self, span_start, span_end, n_segs: int, n_steps: int, bitmap_budget_bytes: int = 0):
+        self.span_start, self.span_end = _u32(span_start), _u32(span_end)
+        self.n_paths, self.n_segs, self.n_steps = int(self.span_start.size), int(n_segs), int(n_steps)
+        h = C.c_void_p()
+        _check(
+            lib().fgfa_depth_plan_create(
+                C.byref(h), self.span_start.ctypes.data, self.span_end.ctypes.data,
+                self.n_paths, self.n_segs, self.n_steps, bitmap_budget_bytes,
+            )
+        )
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().fgfa_depth_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ptr(t) -> Optional[int]:
+        return None if t is None else int(t.data_ptr())
+
+    def run(self, d_steps, d_depth, d_uniq=None, stream: int = 0) -> None:
+        """Enqueue memset + kernel A (+ kernel B) on ``stream``; asynchronous."""
+        _check(lib().fgfa_depth_plan_run(self._h, self._ptr(d_steps), self._ptr(d_depth), self._ptr(d_uniq), stream or None))
+
+    def begin(self, d_depth, stream: int = 0) -> None:
+        _check(lib().fgfa_depth_plan_begin(self._h, self._ptr(d_depth), stream or None))
+
+    def feed(self, d_steps, path_lo: int, path_hi: int, d_depth, d_uniq=None, stream: int = 0) -> None:
+        _check(lib().fgfa_depth_plan_feed(self._h, self._ptr(d_steps), path_lo, path_hi, self._ptr(d_depth), self._ptr(d_uniq), stream or None))
+
+    def finish(self, d_uniq=None, stream: int = 0) -> None:
+        _check(lib().fgfa_depth_plan_finish(self._h, self._ptr(d_uniq), stream or None))
+
+    def status(self, stream: int = 0) -> None:
+        """Synchronise and raise DepthError if a run saw an out-of-range segment id."""
+        _check(lib().fgfa_depth_plan_status(self._h, stream or None))
+
+    def set_probe(self, before_event: int, after_event: int) -> None:
+        """Record the given CUDA events around the next run's step-stream kernel."""
+        _check(lib().fgfa_depth_plan_set_probe(self._h, before_event or None, after_event or None))
+
+    def launches(self, with_uniq: bool = True) -> int:
+        return int(lib().fgfa_depth_plan_launches(self._h, 1 if with_uniq else 0))
+
+    @property
+    def scratch_bytes(self) -> int:
+        return int(lib().fgfa_depth_plan_scratch_bytes(self._h))

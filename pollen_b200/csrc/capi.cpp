@@ -1,0 +1,165 @@
+// C ABI of libflatgfa: the reference's flatgfa-c surface (flatgfa-c/src/lib.rs:62-172)
+// plus the node-depth additions declared in include/flatgfa.h.
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/fgfa_depth.h"
+#include "../../include/flatgfa.h"
+#include "file.hpp"
+#include "ops_depth.hpp"
+#include "parse.hpp"
+
+// lib.rs:16: the opaque store behind flatgfa_t.  Either a parsed heap store or a
+// zero-copy view of a mapped .flatgfa file.
+struct CStore {
+    flatgfa::HeapGFAStore heap;
+    std::unique_ptr<flatgfa::MappedFile> map;
+    flatgfa::FlatGFA gfa;
+};
+
+namespace {
+thread_local std::string g_err;
+flatgfa_string_t null_string() { return flatgfa_string_t{nullptr, 0}; }
+flatgfa_string_t to_string(flatgfa::Pool<uint8_t> p) {
+    return flatgfa_string_t{p.data, (int)p.len()};
+}
+}  // namespace
+
+extern "C" {
+
+const char* flatgfa_last_error(void) { return g_err.c_str(); }
+
+flatgfa_t flatgfa_parse(const char* filename) {
+    if (!filename) { g_err = "null filename"; return nullptr; }
+    try {
+        flatgfa::MappedFile f(filename);                                   // lib.rs:65
+        std::unique_ptr<CStore> s(new CStore());
+        s->heap = flatgfa::Parser::parse_mem(f.data(), f.size());          // lib.rs:66
+        s->gfa = s->heap.view();
+        return s.release();                                                // lib.rs:25-27
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+flatgfa_t flatgfa_load(const char* filename) {
+    if (!filename) { g_err = "null filename"; return nullptr; }
+    try {
+        std::unique_ptr<CStore> s(new CStore());
+        s->map.reset(new flatgfa::MappedFile(filename));
+        s->gfa = flatgfa::file::view_or_throw(s->map->data(), s->map->size());
+        return s.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+void flatgfa_free(flatgfa_t gfa) { delete gfa; }   // lib.rs:71-76 (null-safe)
+
+uint32_t flatgfa_get_segment_count(flatgfa_t gfa) { return (uint32_t)gfa->gfa.segs.len(); }
+
+flatgfa_string_t flatgfa_get_seq(flatgfa_t gfa, uint32_t segment_id) {
+    const auto& g = gfa->gfa;
+    if ((size_t)segment_id >= g.segs.len()) return null_string();          // lib.rs:95-97
+    try {
+        return to_string(g.get_seq(g.segs.data[segment_id]));
+    } catch (const std::exception&) {
+        return null_string();
+    }
+}
+
+uint32_t flatgfa_path_count(flatgfa_t gfa) { return (uint32_t)gfa->gfa.paths.len(); }
+
+flatgfa_string_t flatgfa_get_path_name(flatgfa_t gfa, uint32_t path_index) {
+    const auto& g = gfa->gfa;
+    if ((size_t)path_index >= g.paths.len()) return null_string();         // lib.rs:121-122
+    try {
+        return to_string(g.get_path_name(g.paths.data[path_index]));
+    } catch (const std::exception&) {
+        return null_string();
+    }
+}
+
+uint32_t flatgfa_get_path_step_count(flatgfa_t gfa, uint32_t path_index) {
+    const auto& g = gfa->gfa;
+    if ((size_t)path_index >= g.paths.len()) return UINT32_MAX;            // lib.rs:133-134
+    return (uint32_t)g.paths.data[path_index].step_count();
+}
+
+bool flatgfa_get_step(flatgfa_t gfa, uintptr_t path_index, uintptr_t step_index,
+                      flatgfa_handle_t* out) {
+    const auto& g = gfa->gfa;
+    if (path_index >= g.paths.len()) return false;                         // lib.rs:157-160
+    try {
+        const auto steps = g.get_path_steps(g.paths.data[path_index]);
+        if (step_index >= steps.len()) return false;                       // lib.rs:161-164
+        const flatgfa::Handle h = steps.data[step_index];
+        out->segment_id = h.segment();                                     // lib.rs:167
+        out->is_forward = h.is_forward();                                  // lib.rs:168
+        return true;
+    } catch (const std::exception&) {
+        return false;
+    }
+}
+
+int flatgfa_seg_depth(flatgfa_t gfa, uint64_t* depth, uint64_t* uniq) {
+    if (!gfa || (!depth && gfa->gfa.segs.len())) return FGFA_ERR_INVALID_ARG;
+    const auto& g = gfa->gfa;
+    if (g.segs.len() > 0x7FFFFFFFull || g.paths.len() > 0xFFFFFFFFull || g.steps.len() > 0xFFFFFFFFull)
+        return FGFA_ERR_TOO_LARGE;
+    const uint32_t n_paths = (uint32_t)g.paths.len();
+    std::vector<uint32_t> s(n_paths), e(n_paths);
+    for (uint32_t p = 0; p < n_paths; ++p) {
+        s[p] = g.paths.data[p].steps.start;
+        e[p] = g.paths.data[p].steps.end;
+    }
+    const uint32_t* steps = reinterpret_cast<const uint32_t*>(g.steps.data);
+    std::vector<uint32_t> aligned;
+    if (reinterpret_cast<uintptr_t>(steps) & 3u) {
+        aligned.resize(g.steps.len());
+        std::memcpy(aligned.data(), g.steps.data, g.steps.len() * 4);
+        steps = aligned.data();
+    }
+    int rc = fgfa_seg_depth_with_uniq_steps(steps, g.steps.len(), s.data(), e.data(), n_paths,
+                                            (uint32_t)g.segs.len(), depth, uniq);
+    if (rc) g_err = std::string(fgfa_strerror(rc)) + ": " + fgfa_last_error();
+    return rc;
+}
+
+int flatgfa_format_seg_depth(flatgfa_t gfa, const uint64_t* depth, const uint64_t* uniq, char** out,
+                             size_t* out_len) {
+    if (!gfa || !out || !out_len) return FGFA_ERR_INVALID_ARG;
+    const size_t n = gfa->gfa.segs.len();
+    if (n && (!depth || !uniq)) return FGFA_ERR_INVALID_ARG;
+    flatgfa::ops::depth::SegDepth t{gfa->gfa, std::vector<uint64_t>(depth, depth + n),
+                                    std::vector<uint64_t>(uniq, uniq + n)};
+    std::string s;
+    t.emit(s);
+    char* buf = static_cast<char*>(std::malloc(s.size() + 1));
+    if (!buf) return FGFA_ERR_NOMEM;
+    std::memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+    *out = buf;
+    *out_len = s.size();
+    return FGFA_OK;
+}
+
+int flatgfa_dump(flatgfa_t gfa, const char* filename) {
+    if (!gfa || !filename) return FGFA_ERR_INVALID_ARG;
+    try {
+        std::vector<uint8_t> buf(flatgfa::file::size(gfa->gfa));
+        flatgfa::file::dump(gfa->gfa, buf.data());
+        flatgfa::write_file(filename, buf.data(), buf.size());
+        return FGFA_OK;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return FGFA_ERR_INVALID_ARG;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+// Device plan + C ABI of the B200 node-depth engine (see include/fgfa_depth.h).
+//
+// Replaces the loop nest of the reference's seg_depth_with_uniq / seg_depth
+// (flatgfa/src/ops/depth.rs:15-56) with kernel A (step stream) + kernel B (seen-bitmap
+// population count) from depth_kernels.cuh.  No CPU compute path exists here: every
+// entry point fails with FGFA_ERR_NO_DEVICE when CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fgfa_depth.h"
+#include "depth_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return fail(FGFA_ERR_NO_DEVICE, std::string(what) + ": " + cudaGetErrorString(e));
+    if (e == cudaErrorMemoryAllocation)
+        return fail(FGFA_ERR_NOMEM, std::string(what) + ": " + cudaGetErrorString(e));
+    return fail(FGFA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(x)                                        \
+    do {                                             \
+        cudaError_t e_ = (x);                        \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
+    } while (0)
+
+constexpr size_t kDefaultBitmapBudget = 64ull << 20;  // stays resident in the 126 MB L2
+constexpr int kBlocksPerSM = 6;
+
+}  // namespace
+
+struct fgfa_depth_plan {
+    uint32_t n_paths = 0, n_segs = 0;
+    uint64_t n_steps = 0;
+    std::vector<uint32_t> h_start, h_end;  // host copy of the span table
+    int device = 0, sms = 0;
+    uint32_t n_words = 0, words_per_row = 0, rows_per_batch = 0;
+    uint32_t misalign = 0;                 // d_steps misalignment (elements) the tables are built for
+    uint32_t* d_start = nullptr;           // spans shifted by `misalign`
+    uint32_t* d_end = nullptr;
+    uint32_t* d_prefix = nullptr;          // chunk_prefix[n_paths+1]
+    std::vector<uint32_t> h_prefix;
+    uint32_t* d_bitmap = nullptr;          // [rows_per_batch][words_per_row], zero between runs
+    uint32_t* d_err = nullptr;
+    size_t scratch_bytes = 0;
+    cudaEvent_t probe_before = nullptr, probe_after = nullptr;   // one-shot measurement hook
+    uint32_t next_path = 0;                // begin/feed/finish cursor
+    bool uniq_started = false;
+};
+
+namespace {
+
+int build_tables(fgfa_depth_plan* pl, uint32_t misalign) {
+    const uint32_t n = pl->n_paths;
+    std::vector<uint32_t> s(n), e(n);
+    pl->h_prefix.assign((size_t)n + 1, 0u);
+    uint64_t chunks = 0;
+    for (uint32_t p = 0; p < n; ++p) {
+        const uint64_t sp = (uint64_t)pl->h_start[p] + misalign, ep = (uint64_t)pl->h_end[p] + misalign;
+        if (ep > 0xFFFFFFFFull) return fail(FGFA_ERR_TOO_LARGE, "steps pool too large for a misaligned device pointer");
+        s[p] = (uint32_t)sp;
+        e[p] = (uint32_t)ep;
+        if (ep > sp) chunks += (ep - (sp & ~3ull) + fgfa::kChunk - 1) / fgfa::kChunk;
+        if (chunks > 0xFFFFFFFFull) return fail(FGFA_ERR_TOO_LARGE, "too many chunks");
+        pl->h_prefix[p + 1] = (uint32_t)chunks;
+    }
+    if (n) {
+        CU(cudaMemcpy(pl->d_start, s.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(pl->d_end, e.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(pl->d_prefix, pl->h_prefix.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
+    pl->misalign = misalign;
+    return FGFA_OK;
+}
+
+// kernel A over paths [lo, hi), which must lie inside one bitmap batch.
+int launch_stream(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t lo, uint32_t hi,
+                  uint32_t* d_depth, bool with_seen, cudaStream_t st) {
+    const uint32_t chunks = pl->h_prefix[hi] - pl->h_prefix[lo];
+    if (chunks == 0) return FGFA_OK;
+    fgfa::StreamParams P{};
+    P.steps = d_steps_aligned;
+    P.n_steps = pl->n_steps + pl->misalign;
+    P.span_start = pl->d_start;
+    P.span_end = pl->d_end;
+    P.chunk_prefix = pl->d_prefix;
+    P.path_lo = lo;
+    P.path_hi = hi;
+    P.n_segs = pl->n_segs;
+    P.words_per_row = pl->words_per_row;
+    P.depth = d_depth;
+    P.bitmap = with_seen ? pl->d_bitmap + (size_t)(lo % pl->rows_per_batch) * pl->words_per_row : nullptr;
+    P.err = pl->d_err;
+    const uint32_t grid = std::min<uint32_t>(chunks, (uint32_t)pl->sms * kBlocksPerSM);
+    if (pl->probe_before) CU(cudaEventRecord(pl->probe_before, st));
+    if (with_seen)
+        fgfa::k_step_stream_merged<kBlocksPerSM, true><<<grid, fgfa::kThreads, 0, st>>>(P);
+    else
+        fgfa::k_step_stream_merged<kBlocksPerSM, false><<<grid, fgfa::kThreads, 0, st>>>(P);
+    CU(cudaGetLastError());
+    if (pl->probe_after) CU(cudaEventRecord(pl->probe_after, st));
+    pl->probe_before = pl->probe_after = nullptr;
+    return FGFA_OK;
+}
+
+// kernel B over the first `rows` rows of the bitmap scratch.
+int launch_popcount(fgfa_depth_plan* pl, uint32_t rows, uint32_t* d_uniq, bool accumulate, cudaStream_t st) {
+    if (pl->n_words == 0) return FGFA_OK;
+    fgfa::PopcountParams Q{};
+    Q.bitmap = pl->d_bitmap;
+    Q.n_rows = rows;
+    Q.words_per_row = pl->words_per_row;
+    Q.n_words = pl->n_words;
+    Q.n_segs = pl->n_segs;
+    Q.uniq = d_uniq;
+    Q.depth = nullptr;
+    Q.accumulate = accumulate ? 1 : 0;
+    const uint32_t grid = (pl->n_words + fgfa::kPopThreads - 1) / fgfa::kPopThreads;
+    fgfa::k_uniq_popcount<<<grid, fgfa::kPopThreads, 0, st>>>(Q);
+    CU(cudaGetLastError());
+    return FGFA_OK;
+}
+
+int prepare_pointer(fgfa_depth_plan* pl, const uint32_t* d_steps, const uint32_t** aligned) {
+    const uintptr_t addr = (uintptr_t)d_steps;
+    if (addr & 3u) return fail(FGFA_ERR_INVALID_ARG, "d_steps must be 4-byte aligned");
+    const uint32_t mis = (uint32_t)((addr >> 2) & 3u);
+    if (mis != pl->misalign) {
+        // Rare: the pool does not start on a 16-byte boundary.  Shift the span table so
+        // that the kernels can keep issuing aligned 128-bit loads from the rounded-down base.
+        CU(cudaDeviceSynchronize());
+        int rc = build_tables(pl, mis);
+        if (rc) return rc;
+    }
+    *aligned = d_steps - mis;
+    return FGFA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fgfa_strerror(int code) {
+    switch (code) {
+        case FGFA_OK: return "ok";
+        case FGFA_ERR_INVALID_ARG: return "invalid argument";
+        case FGFA_ERR_BAD_MAGIC: return "not a FlatGFA file (bad magic number)";
+        case FGFA_ERR_TRUNCATED: return "FlatGFA image is truncated or its table of contents is inconsistent";
+        case FGFA_ERR_SPAN_OOB: return "a path's steps span lies outside the steps pool";
+        case FGFA_ERR_SEG_OOB: return "a step refers to a segment index outside the segs pool";
+        case FGFA_ERR_CUDA: return "CUDA error";
+        case FGFA_ERR_NOMEM: return "out of memory";
+        case FGFA_ERR_NO_DEVICE: return "no CUDA device available (this library has no CPU path)";
+        case FGFA_ERR_TOO_LARGE: return "graph too large for the format's 32-bit ids";
+        default: return "unknown error";
+    }
+}
+
+const char* fgfa_last_error(void) { return g_last_error.c_str(); }
+
+int fgfa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start,
+                           const uint32_t* h_span_end, uint32_t n_paths, uint32_t n_segs,
+                           uint64_t n_steps, size_t bitmap_budget_bytes) {
+    if (!out || (n_paths && (!h_span_start || !h_span_end))) return fail(FGFA_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (n_steps > 0xFFFFFFFFull || n_segs > 0x7FFFFFFFu) return fail(FGFA_ERR_TOO_LARGE, "counts exceed u32 ids");
+    for (uint32_t p = 0; p < n_paths; ++p)  // pool.rs:341-347: slicing panics outside the pool
+        if (h_span_start[p] > h_span_end[p] || (uint64_t)h_span_end[p] > n_steps)
+            return fail(FGFA_ERR_SPAN_OOB, "path " + std::to_string(p) + " has a steps span outside the pool");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    fgfa_depth_plan* pl = new (std::nothrow) fgfa_depth_plan();
+    if (!pl) return fail(FGFA_ERR_NOMEM, "plan allocation failed");
+    pl->n_paths = n_paths;
+    pl->n_segs = n_segs;
+    pl->n_steps = n_steps;
+    pl->h_start.assign(h_span_start, h_span_start + n_paths);
+    pl->h_end.assign(h_span_end, h_span_end + n_paths);
+    pl->device = dev;
+    auto bail = [&](int rc) { fgfa_depth_plan_destroy(pl); return rc; };
+    {
+        cudaError_t e = cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaDeviceGetAttribute"));
+    }
+    pl->n_words = (n_segs + 31) / 32;
+    pl->words_per_row = (pl->n_words + 31) & ~31u;  // 128-byte row pitch
+    const size_t row_bytes = (size_t)pl->words_per_row * 4;
+    const size_t budget = bitmap_budget_bytes ? bitmap_budget_bytes : kDefaultBitmapBudget;
+    uint64_t rows = row_bytes ? std::max<uint64_t>(1, budget / row_bytes) : 1;
+    rows = std::min<uint64_t>(rows, std::max<uint32_t>(1u, n_paths));
+    pl->rows_per_batch = (uint32_t)rows;
+    const size_t bitmap_bytes = std::max<size_t>(row_bytes * rows, 4);
+#define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(cuda_fail(e_, #x)); } while (0)
+    CUB_(cudaMalloc(&pl->d_start, std::max<size_t>((size_t)n_paths * 4, 4)));
+    CUB_(cudaMalloc(&pl->d_end, std::max<size_t>((size_t)n_paths * 4, 4)));
+    CUB_(cudaMalloc(&pl->d_prefix, ((size_t)n_paths + 1) * 4));
+    CUB_(cudaMalloc(&pl->d_bitmap, bitmap_bytes));
+    CUB_(cudaMalloc(&pl->d_err, 4));
+    CUB_(cudaMemset(pl->d_bitmap, 0, bitmap_bytes));
+    CUB_(cudaMemset(pl->d_err, 0, 4));
+#undef CUB_
+    pl->scratch_bytes = bitmap_bytes + (size_t)n_paths * 12 + 8;
+    int rc = build_tables(pl, 0);
+    if (rc) return bail(rc);
+    *out = pl;
+    return FGFA_OK;
+}
+
+void fgfa_depth_plan_destroy(fgfa_depth_plan_t* pl) {
+    if (!pl) return;
+    cudaFree(pl->d_start);
+    cudaFree(pl->d_end);
+    cudaFree(pl->d_prefix);
+    cudaFree(pl->d_bitmap);
+    cudaFree(pl->d_err);
+    delete pl;
+}
+
+int fgfa_depth_plan_begin(fgfa_depth_plan_t* pl, uint32_t* d_depth, void* cuda_stream) {
+    if (!pl || (!d_depth && pl->n_segs)) return fail(FGFA_ERR_INVALID_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (pl->n_segs) CU(cudaMemsetAsync(d_depth, 0, (size_t)pl->n_segs * 4, st));  // depth.rs:17 vec![0; n]
+    pl->next_path = 0;
+    pl->uniq_started = false;
+    return FGFA_OK;
+}
+
+int fgfa_depth_plan_feed(fgfa_depth_plan_t* pl, const uint32_t* d_steps, uint32_t path_lo,
+                         uint32_t path_hi, uint32_t* d_depth, uint32_t* d_uniq, void* cuda_stream) {
+    if (!pl || (!d_depth && pl->n_segs)) return fail(FGFA_ERR_INVALID_ARG, "null argument");
+    if (path_lo != pl->next_path || path_hi < path_lo || path_hi > pl->n_paths)
+        return fail(FGFA_ERR_INVALID_ARG, "paths must be fed contiguously and in order");
+    if (!d_steps && pl->n_steps) return fail(FGFA_ERR_INVALID_ARG, "d_steps is null");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint32_t* base = d_steps;
+    if (pl->n_steps) {
+        int rc = prepare_pointer(pl, d_steps, &base);
+        if (rc) return rc;
+    }
+    const bool with_seen = d_uniq != nullptr;
+    uint32_t lo = path_lo;
+    while (lo < path_hi) {
+        const uint32_t batch_end = std::min<uint64_t>(pl->n_paths, ((uint64_t)lo / pl->rows_per_batch + 1) * pl->rows_per_batch);
+        const uint32_t hi = std::min(path_hi, batch_end);
+        int rc = launch_stream(pl, base, lo, hi, d_depth, with_seen, st);
+        if (rc) return rc;
+        if (with_seen && hi == batch_end) {  // this bitmap batch is complete: fold it into uniq
+            const uint32_t batch_start = (lo / pl->rows_per_batch) * pl->rows_per_batch;
+            rc = launch_popcount(pl, batch_end - batch_start, d_uniq, pl->uniq_started, st);
+            if (rc) return rc;
+            pl->uniq_started = true;
+        }
+        lo = hi;
+    }
+    pl->next_path = path_hi;
+    return FGFA_OK;
+}
+
+int fgfa_depth_plan_finish(fgfa_depth_plan_t* pl, uint32_t* d_uniq, void* cuda_stream) {
+    if (!pl) return fail(FGFA_ERR_INVALID_ARG, "null plan");
+    if (pl->next_path != pl->n_paths) return fail(FGFA_ERR_INVALID_ARG, "not all paths were fed");
+    if (d_uniq && !pl->uniq_started && pl->n_segs)  // no paths at all: uniq is all zero
+        CU(cudaMemsetAsync(d_uniq, 0, (size_t)pl->n_segs * 4, (cudaStream_t)cuda_stream));
+    return FGFA_OK;
+}
+
+int fgfa_depth_plan_run(fgfa_depth_plan_t* pl, const uint32_t* d_steps, uint32_t* d_depth,
+                        uint32_t* d_uniq, void* cuda_stream) {
+    int rc = fgfa_depth_plan_begin(pl, d_depth, cuda_stream);
+    if (rc) return rc;
+    rc = fgfa_depth_plan_feed(pl, d_steps, 0, pl->n_paths, d_depth, d_uniq, cuda_stream);
+    if (rc) return rc;
+    return fgfa_depth_plan_finish(pl, d_uniq, cuda_stream);
+}
+
+int fgfa_depth_plan_status(fgfa_depth_plan_t* pl, void* cuda_stream) {
+    if (!pl) return fail(FGFA_ERR_INVALID_ARG, "null plan");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    uint32_t flag = 0;
+    CU(cudaMemcpyAsync(&flag, pl->d_err, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flag) {
+        CU(cudaMemsetAsync(pl->d_err, 0, 4, st));
+        CU(cudaStreamSynchronize(st));
+        return fail(FGFA_ERR_SEG_OOB, "a step refers to a segment index >= n_segs");
+    }
+    return FGFA_OK;
+}
+
+int fgfa_depth_plan_set_probe(fgfa_depth_plan_t* pl, void* before, void* after) {
+    if (!pl) return fail(FGFA_ERR_INVALID_ARG, "null plan");
+    pl->probe_before = (cudaEvent_t)before;
+    pl->probe_after = (cudaEvent_t)after;
+    return FGFA_OK;
+}
+
+uint32_t fgfa_depth_plan_launches(const fgfa_depth_plan_t* pl, int with_uniq) {
+    if (!pl || pl->n_paths == 0) return 0;
+    const uint32_t batches = (pl->n_paths + pl->rows_per_batch - 1) / pl->rows_per_batch;
+    return with_uniq ? 2 * batches : batches;
+}
+
+size_t fgfa_depth_plan_scratch_bytes(const fgfa_depth_plan_t* pl) { return pl ? pl->scratch_bytes : 0; }
+
+int fgfa_depth_device(const uint32_t* d_steps, uint64_t n_steps, const uint32_t* d_span_start,
+                      const uint32_t* d_span_end, uint32_t n_paths, uint32_t n_segs,
+                      uint32_t* d_depth, uint32_t* d_uniq, void* cuda_stream) {
+    if (n_paths && (!d_span_start || !d_span_end)) return fail(FGFA_ERR_INVALID_ARG, "null span table");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    std::vector<uint32_t> s(n_paths), e(n_paths);
+    if (n_paths) {
+        CU(cudaMemcpyAsync(s.data(), d_span_start, (size_t)n_paths * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(e.data(), d_span_end, (size_t)n_paths * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    fgfa_depth_plan_t* pl = nullptr;
+    int rc = fgfa_depth_plan_create(&pl, s.data(), e.data(), n_paths, n_segs, n_steps, 0);
+    if (rc) return rc;
+    rc = fgfa_depth_plan_run(pl, d_steps, d_depth, d_uniq, cuda_stream);
+    if (rc == FGFA_OK) rc = fgfa_depth_plan_status(pl, cuda_stream);
+    fgfa_depth_plan_destroy(pl);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// `fgfa` command-line tool, restricted to what the node-depth path needs.
+//
+// Mirrors the reference CLI's spelling (flatgfa/src/cli/main.rs:7-55 global options,
+// flatgfa/src/cli/cmds.rs:217-232 `depth` options, main.rs:87-138 input loading and
+// dispatch, main.rs:190-213 `dump`):
+//   fgfa [-i FLATGFA | -I GFA | < GFA] depth -d          node-depth table on stdout
+//   fgfa [-i FLATGFA | -I GFA | < GFA] -o OUT.flatgfa    convert to the binary format
+// The other thirteen subcommands of the reference are outside this repository's scope
+// and are rejected with an error.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "file.hpp"
+#include "ops_depth.hpp"
+#include "parse.hpp"
+
+namespace {
+
+struct Args {
+    std::string input, input_gfa, output, output_gfa;   // -i -I -o -O
+    bool mutate = false;                                // -m
+    size_t prealloc_factor = 32;                        // -p
+    std::string command;
+    // depth (cmds.rs:217-232)
+    bool seg_depth = false;                             // -d / --graph-depth-table
+    std::vector<std::string> paths;                     // -r
+    std::string bed;                                    // -b / --bed-input
+};
+
+int usage(const char* msg) {
+    if (msg) std::fprintf(stderr, "%s\n", msg);
+    std::fprintf(stderr,
+                 "Usage: fgfa [-i <input>] [-I <input-gfa>] [-o <output>] [-O <output-gfa>] [-m] "
+                 "[-p <prealloc-factor>] [<command>] [<args>]\n\n"
+                 "Convert between GFA text and FlatGFA binary formats.\n\n"
+                 "Commands:\n  depth             compute depth: the number of times paths cross a node\n"
+                 "                    -d, --graph-depth-table  compute node depth instead of path depth\n");
+    return 1;
+}
+
+bool take(int& i, int argc, char** argv, std::string& dst) {
+    if (i + 1 >= argc) return false;
+    dst = argv[++i];
+    return true;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Args a;
+    int i = 1;
+    for (; i < argc; ++i) {   // global options, up to the subcommand (main.rs:7-36)
+        const std::string t = argv[i];
+        if (t == "-i") { if (!take(i, argc, argv, a.input)) return usage("No value provided for option '-i'."); }
+        else if (t == "-I") { if (!take(i, argc, argv, a.input_gfa)) return usage("No value provided for option '-I'."); }
+        else if (t == "-o") { if (!take(i, argc, argv, a.output)) return usage("No value provided for option '-o'."); }
+        else if (t == "-O") { if (!take(i, argc, argv, a.output_gfa)) return usage("No value provided for option '-O'."); }
+        else if (t == "-m") a.mutate = true;
+        else if (t == "-p") { std::string v; if (!take(i, argc, argv, v)) return usage("No value provided for option '-p'."); a.prealloc_factor = std::stoul(v); }
+        else if (t == "--help" || t == "help") { usage(nullptr); return 0; }
+        else if (!t.empty() && t[0] == '-') return usage(("Unrecognized argument: " + t).c_str());
+        else { a.command = t; ++i; break; }
+    }
+    if (a.command == "depth") {
+        for (; i < argc; ++i) {
+            const std::string t = argv[i];
+            if (t == "-d" || t == "--graph-depth-table") a.seg_depth = true;
+            else if (t == "-r") { std::string v; if (!take(i, argc, argv, v)) return usage("No value provided for option '-r'."); a.paths.push_back(v); }
+            else if (t == "-b" || t == "--bed-input") { if (!take(i, argc, argv, a.bed)) return usage("No value provided for option '-b'."); }
+            else return usage(("Unrecognized argument: " + t).c_str());
+        }
+    } else if (!a.command.empty()) {
+        std::fprintf(stderr, "fgfa: subcommand '%s' is outside the scope of this build (node depth only)\n",
+                     a.command.c_str());
+        return 1;
+    }
+    if (a.mutate) {
+        std::fprintf(stderr, "fgfa: in-place mutation (-m) is outside the scope of this build\n");
+        return 1;
+    }
+
+    try {
+        // Load the input from a file (binary) or stdin (text): main.rs:87-117.
+        std::unique_ptr<flatgfa::MappedFile> map;
+        flatgfa::HeapGFAStore store;
+        flatgfa::FlatGFA gfa;
+        if (!a.input.empty()) {
+            map.reset(new flatgfa::MappedFile(a.input));                      // main.rs:99
+            gfa = flatgfa::file::view_or_throw(map->data(), map->size());     // main.rs:100
+        } else if (!a.input_gfa.empty()) {
+            flatgfa::MappedFile text(a.input_gfa);                            // main.rs:106
+            store = flatgfa::Parser::parse_mem(text.data(), text.size());     // main.rs:107
+            gfa = store.view();
+        } else {
+            store = flatgfa::Parser::parse_stream(stdin);                     // main.rs:110-111
+            gfa = store.view();
+        }
+
+        if (a.command == "depth") {                                           // main.rs:136-138
+            if (!a.seg_depth) {
+                std::fprintf(stderr, "fgfa depth: only the node-depth table (-d) is implemented in this build\n");
+                return 1;
+            }
+            auto du = flatgfa::ops::depth::seg_depth_with_uniq(gfa);          // cmds.rs:239
+            flatgfa::ops::depth::SegDepth{gfa, std::move(du.first), std::move(du.second)}.print();  // cmds.rs:240-245
+            return 0;
+        }
+
+        // No command: emit the graph (main.rs:181-184, 190-213).
+        if (!a.output.empty()) {
+            std::vector<uint8_t> buf(flatgfa::file::size(gfa));
+            flatgfa::file::dump(gfa, buf.data());
+            flatgfa::write_file(a.output, buf.data(), buf.size());
+            return 0;
+        }
+        std::fprintf(stderr, "fgfa: GFA text output is outside the scope of this build; use -o <file.flatgfa>\n");
+        return 1;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+}

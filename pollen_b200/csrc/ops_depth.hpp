@@ -1,0 +1,40 @@
+// The node-depth op, host side.  Same names and semantics as the reference's
+// flatgfa/src/ops/depth.rs:15-82 (`seg_depth_with_uniq`, `seg_depth`, `SegDepth` +
+// `Emit`), with the loop nest executed by the sm_100a kernels behind fgfa_depth.h.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "flatgfa.hpp"
+
+namespace flatgfa {
+namespace ops {
+namespace depth {
+
+// depth.rs:15-39.  Both vectors have gfa.segs.len() entries, indexed by segment pool
+// index; values are `usize` (u64).  Throws flatgfa::Error on device failure or where the
+// reference would panic (span / segment index out of range).
+std::pair<std::vector<uint64_t>, std::vector<uint64_t>> seg_depth_with_uniq(const FlatGFA& gfa);
+
+// depth.rs:45-56.
+std::vector<uint64_t> seg_depth(const FlatGFA& gfa);
+
+// depth.rs:61-82: the odgi-style TSV table.
+struct SegDepth {
+    const FlatGFA& gfa;
+    std::vector<uint64_t> depths;
+    std::vector<uint64_t> uniq_depths;
+
+    // emit.rs:8-19 `Emit`: header `#node.id\tdepth\tdepth.uniq`, then one row per segment
+    // in pool order with `seg.name as u32` (truncating cast, depth.rs:71).
+    void emit(std::string& out) const;
+    void emit(FILE* f) const;
+    void print() const { emit(stdout); }   // emit.rs:13-18
+};
+
+}  // namespace depth
+}  // namespace ops
+}  // namespace flatgfa

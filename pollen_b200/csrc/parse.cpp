@@ -1,0 +1,227 @@
+#include "parse.hpp"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace flatgfa {
+
+void NameMap::insert(uint64_t name, uint32_t id) {
+    // namemap.rs:17-25 (release-build arithmetic: `name - 1` wraps for name == 0).
+    if ((name - 1) == sequential_max_ && (name - 1) == (uint64_t)id) {
+        sequential_max_ += 1;
+    } else {
+        others_[name] = id;   // HashMap::insert overwrites
+    }
+}
+
+uint32_t NameMap::get(uint64_t name) const {
+    if (name <= sequential_max_) return (uint32_t)(name - 1);   // namemap.rs:28-29 (`as u32` truncates)
+    auto it = others_.find(name);
+    if (it == others_.end()) throw Error("unknown segment name " + std::to_string(name));
+    return it->second;
+}
+
+namespace {
+
+struct Cursor {
+    const uint8_t* p;
+    size_t n;
+    bool empty() const { return n == 0; }
+    void advance(size_t k) { p += k; n -= k; }
+};
+
+// atoi::FromRadix10 (unchecked): leading decimal digits, wrapping arithmetic.
+template <typename T>
+T parse_num(Cursor& c) {   // gfaline.rs:158-164
+    T v = 0;
+    size_t used = 0;
+    while (used < c.n && c.p[used] >= '0' && c.p[used] <= '9') {
+        v = (T)(v * 10 + (T)(c.p[used] - '0'));
+        ++used;
+    }
+    if (used == 0) throw Error("expected number");
+    c.advance(used);
+    return v;
+}
+
+void parse_byte(Cursor& c, uint8_t b) {   // gfaline.rs:150-155
+    if (c.empty() || c.p[0] != b) throw Error("expected byte");
+    c.advance(1);
+}
+
+// gfaline.rs:133-147: up to the next tab (consumed) or the end of the line.
+Cursor parse_field(Cursor& c) {
+    const void* t = c.n ? std::memchr(c.p, '\t', c.n) : nullptr;
+    size_t end = t ? (size_t)((const uint8_t*)t - c.p) : c.n;
+    Cursor f{c.p, end};
+    if (end == c.n) c.advance(c.n); else c.advance(end + 1);
+    return f;
+}
+
+bool parse_orient(Cursor& c) {   // gfaline.rs:167-177; true = forward
+    if (c.empty()) throw Error("expected orientation");
+    const uint8_t b = c.p[0];
+    if (b != '+' && b != '-') throw Error("expected orient");
+    c.advance(1);
+    return b == '+';
+}
+
+AlignOp parse_align_op(Cursor& c) {   // gfaline.rs:180-190; flatgfa.rs:229-234
+    const uint32_t len = parse_num<uint32_t>(c);
+    if (c.empty()) throw Error("expected align op");   // reference: index panic
+    uint32_t op;
+    switch (c.p[0]) {   // enum order Match, Gap, Insertion, Deletion (flatgfa.rs:213-218)
+        case 'M': op = 0; break;
+        case 'N': op = 1; break;
+        case 'D': op = 3; break;   // gfaline.rs:185: 'D' => Deletion
+        case 'I': op = 2; break;   // gfaline.rs:186: 'I' => Insertion
+        default: throw Error("expected align op");
+    }
+    if (len & ~0xFFu) throw Error("length too large");   // flatgfa.rs:231
+    c.advance(1);
+    return AlignOp{(len << 8) | op};
+}
+
+std::vector<AlignOp> parse_align(Cursor& c) {   // gfaline.rs:195-204
+    std::vector<AlignOp> a;
+    while (!c.empty() && c.p[0] >= '0' && c.p[0] <= '9') a.push_back(parse_align_op(c));
+    return a;
+}
+
+std::vector<std::vector<AlignOp>> parse_maybe_overlap_list(Cursor& c) {   // gfaline.rs:103-126
+    std::vector<std::vector<AlignOp>> out;
+    if (c.n == 1 && c.p[0] == '*') { c.advance(1); return out; }
+    while (!c.empty()) {
+        out.push_back(parse_align(c));
+        if (!c.empty()) parse_byte(c, ',');
+    }
+    return out;
+}
+
+struct Builder {
+    HeapGFAStore flat;
+    NameMap seg_ids;
+
+    static Cursor body(const uint8_t* line, size_t n) {   // gfaline.rs:37-41
+        if (n < 2 || line[1] != '\t') throw Error("expected marker and tab");
+        return Cursor{line + 2, n - 2};
+    }
+
+    void header(const uint8_t* line, size_t n) {   // gfaline.rs:52-54; parse.rs:44-46
+        Cursor c = body(line, n);
+        flat.add_header(c.p, c.n);
+    }
+    void segment(const uint8_t* line, size_t n) {   // gfaline.rs:57-62; parse.rs:138-141
+        Cursor c = body(line, n);
+        const uint64_t name = parse_num<uint64_t>(c);
+        parse_byte(c, '\t');
+        Cursor seq = parse_field(c);
+        const uint32_t id = flat.add_seg(name, seq.p, seq.n, c.p, c.n);
+        seg_ids.insert(name, id);
+    }
+    void link(const uint8_t* line, size_t n) {   // gfaline.rs:65-85; parse.rs:143-147
+        Cursor c = body(line, n);
+        const uint64_t from_seg = parse_num<uint64_t>(c);
+        parse_byte(c, '\t');
+        const bool from_fwd = parse_orient(c);
+        parse_byte(c, '\t');
+        const uint64_t to_seg = parse_num<uint64_t>(c);
+        parse_byte(c, '\t');
+        const bool to_fwd = parse_orient(c);
+        parse_byte(c, '\t');
+        std::vector<AlignOp> overlap = parse_align(c);
+        if (!c.empty()) throw Error("expected end of line");
+        const Handle from = Handle::make(seg_ids.get(from_seg), from_fwd);
+        const Handle to = Handle::make(seg_ids.get(to_seg), to_fwd);
+        flat.add_link(from, to, overlap);
+    }
+    void path(const uint8_t* line, size_t n) {   // gfaline.rs:88-100; parse.rs:149-159
+        Cursor c = body(line, n);
+        Cursor name = parse_field(c);
+        Cursor steps = parse_field(c);
+        std::vector<std::vector<AlignOp>> overlaps = parse_maybe_overlap_list(c);
+        if (!c.empty()) throw Error("expected end of line");
+        const uint32_t start = HeapGFAStore::id(flat.steps.size());
+        const size_t used = parse_steps(steps.p, steps.n, [&](uint64_t seg, bool fwd) {
+            flat.steps.push_back(Handle::make(seg_ids.get(seg), fwd));
+        });
+        if (used != steps.n) throw Error("malformed step list");   // parse.rs:155 assert
+        const Span span{start, HeapGFAStore::id(flat.steps.size())};
+        flat.add_path(name.p, name.n, span, overlaps);
+    }
+    void other(const uint8_t* line, size_t n) {   // gfaline.rs:37-49 for H / S / anything else
+        if (n < 2 || line[1] != '\t') throw Error("expected marker and tab");
+        switch (line[0]) {
+            case 'H': flat.record_line(kLineHeader); header(line, n); break;
+            case 'S': flat.record_line(kLineSegment); segment(line, n); break;
+            default: throw Error("unhandled line kind");
+        }
+    }
+};
+
+}  // namespace
+
+HeapGFAStore Parser::parse_mem(const uint8_t* buf, size_t len) {
+    Builder b;
+    std::vector<std::pair<const uint8_t*, size_t>> deferred;
+    size_t pos = 0;
+    while (pos < len) {   // memfile.rs:50-61
+        const void* nl = std::memchr(buf + pos, '\n', len - pos);
+        if (!nl) break;   // final line without a newline is dropped
+        const uint8_t* line = buf + pos;
+        const size_t n = (size_t)((const uint8_t*)nl - line);
+        pos += n + 1;
+        if (n == 0) throw Error("empty line");   // reference: line[0] index panic
+        if (line[0] == 'P' || line[0] == 'L') {   // parse.rs:83-91
+            b.flat.record_line(line[0] == 'P' ? kLinePath : kLineLink);
+            deferred.emplace_back(line, n);
+            continue;
+        }
+        b.other(line, n);
+    }
+    for (auto& d : deferred) {   // parse.rs:110-123: in file order
+        if (d.first[0] == 'L') b.link(d.first, d.second); else b.path(d.first, d.second);
+    }
+    return std::move(b.flat);
+}
+
+HeapGFAStore Parser::parse_stream(FILE* in) {
+    Builder b;
+    std::vector<std::string> links, paths;
+    std::string line;
+    auto handle = [&](const std::string& ln) {
+        if (ln.empty()) throw Error("empty line");
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(ln.data());
+        if (ln[0] == 'P') {   // parse.rs:35-39: paths are kept as raw lines
+            b.flat.record_line(kLinePath);
+            paths.push_back(ln);
+        } else if (ln[0] == 'L') {   // parse.rs:42-43,52-54: parsed now in the reference, added later
+            if (ln.size() < 2 || ln[1] != '\t') throw Error("expected marker and tab");
+            b.flat.record_line(kLineLink);
+            links.push_back(ln);
+        } else {
+            b.other(p, ln.size());
+        }
+    };
+    char chunk[1 << 16];
+    size_t got;
+    while ((got = std::fread(chunk, 1, sizeof chunk, in)) > 0) {
+        size_t start = 0;
+        for (size_t i = 0; i < got; ++i) {
+            if (chunk[i] == '\n') {
+                line.append(chunk + start, i - start);
+                handle(line);
+                line.clear();
+                start = i + 1;
+            }
+        }
+        line.append(chunk + start, got - start);
+    }
+    if (!line.empty()) handle(line);   // BufRead::split yields an unterminated last line
+    for (auto& l : links) b.link(reinterpret_cast<const uint8_t*>(l.data()), l.size());   // parse.rs:61-63
+    for (auto& p : paths) b.path(reinterpret_cast<const uint8_t*>(p.data()), p.size());   // parse.rs:64-70
+    return std::move(b.flat);
+}
+
+}  // namespace flatgfa

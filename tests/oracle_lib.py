@@ -1,0 +1,117 @@
+"""Test-side access to the ORACLE (oracle/depth_oracle.c) and a tiny independent GFA
+reader.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+legs may use this; the product never does."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+def oracle():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "libdepth_oracle.so")
+        h = C.CDLL(path)
+        h.oracle_seg_depth_with_uniq.restype = C.c_int
+        h.oracle_seg_depth_with_uniq.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        h.oracle_seg_depth.restype = C.c_int
+        h.oracle_seg_depth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        h.oracle_file_seg_depth_with_uniq.restype = C.c_int
+        h.oracle_file_seg_depth_with_uniq.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        h.oracle_file_seg_names.restype = C.c_int
+        h.oracle_file_seg_names.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        h.oracle_emit_seg_depth.restype = C.c_int64
+        h.oracle_emit_seg_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint64]
+
+        class View(C.Structure):
+            _fields_ = [(n, C.c_uint64) for n in ("n_segs", "n_paths", "n_steps", "segs_off", "paths_off", "steps_off")]
+
+        h.View = View
+        h.oracle_view.restype = C.c_int
+        h.oracle_view.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(View)]
+        _LIB = h
+    return _LIB
+
+
+def spans_of(start, end):
+    s = np.empty(2 * len(start), dtype=np.uint32)
+    s[0::2] = start
+    s[1::2] = end
+    return s
+
+
+def depth_with_uniq(steps, start, end, n_segs):
+    """oracle_seg_depth_with_uniq -> (rc, depth u64, uniq u64)."""
+    steps = np.ascontiguousarray(steps, dtype=np.uint32)
+    sp = spans_of(start, end)
+    d = np.empty(n_segs, dtype=np.uint64)
+    u = np.empty(n_segs, dtype=np.uint64)
+    rc = oracle().oracle_seg_depth_with_uniq(steps.ctypes.data, steps.size, sp.ctypes.data, len(start), n_segs, d.ctypes.data, u.ctypes.data)
+    return rc, d, u
+
+
+def depth_only(steps, start, end, n_segs):
+    steps = np.ascontiguousarray(steps, dtype=np.uint32)
+    sp = spans_of(start, end)
+    d = np.empty(n_segs, dtype=np.uint64)
+    rc = oracle().oracle_seg_depth(steps.ctypes.data, steps.size, sp.ctypes.data, len(start), n_segs, d.ctypes.data)
+    return rc, d
+
+
+def file_depth(image: bytes):
+    """Oracle over a .flatgfa image -> (rc, names, depth, uniq)."""
+    o = oracle()
+    buf = np.frombuffer(image, dtype=np.uint8)
+    v = o.View()
+    rc = o.oracle_view(buf.ctypes.data, buf.size, C.byref(v))
+    if rc:
+        return rc, None, None, None
+    n = int(v.n_segs)
+    names = np.empty(n, dtype=np.uint64)
+    d = np.empty(n, dtype=np.uint64)
+    u = np.empty(n, dtype=np.uint64)
+    rc = o.oracle_file_seg_depth_with_uniq(buf.ctypes.data, buf.size, d.ctypes.data, u.ctypes.data)
+    if rc:
+        return rc, None, None, None
+    o.oracle_file_seg_names(buf.ctypes.data, buf.size, names.ctypes.data)
+    return 0, names, d, u
+
+
+def emit(names, depth, uniq) -> bytes:
+    n = len(names)
+    cap = 64 + 64 * n
+    out = C.create_string_buffer(cap)
+    names = np.ascontiguousarray(names, dtype=np.uint64)
+    depth = np.ascontiguousarray(depth, dtype=np.uint64)
+    uniq = np.ascontiguousarray(uniq, dtype=np.uint64)
+    k = oracle().oracle_emit_seg_depth(names.ctypes.data, depth.ctypes.data, uniq.ctypes.data, n, out, cap)
+    assert k >= 0
+    return out.raw[:k]
+
+
+def read_gfa(text: str):
+    """Independent minimal GFA reader for pinning the oracle (not the product parser):
+    segment pool index = order of S lines (flatgfa/src/parse.rs:138-141), steps in P-line
+    order, Handle = index << 1 | (orientation == '-') (flatgfa/src/flatgfa.rs:192-198).
+    Returns (names, steps, start, end, path_names)."""
+    names, index = [], {}
+    for line in text.split("\n"):
+        f = line.split("\t")
+        if f[0] == "S":
+            index[f[1]] = len(names)
+            names.append(int(f[1]))
+    steps, start, end, pnames = [], [], [], []
+    for line in text.split("\n"):
+        f = line.split("\t")
+        if f[0] == "P":
+            pnames.append(f[1])
+            start.append(len(steps))
+            for tok in f[2].split(","):
+                if tok:
+                    steps.append((index[tok[:-1]] << 1) | (1 if tok[-1] == "-" else 0))
+            end.append(len(steps))
+    return (np.array(names, dtype=np.uint64), np.array(steps, dtype=np.uint32),
+            np.array(start, dtype=np.uint32), np.array(end, dtype=np.uint32), pnames)

@@ -1,0 +1,220 @@
+"""Host-side logic that needs no GPU: the .flatgfa reader/writer, the GFA text parser,
+the flatgfa-c accessors, the CLI's conversion mode, and the C ABI's export list."""
+import ctypes as C
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import pollen_b200 as pb
+from pollen_b200 import binding, flatgfa_io, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_every_declared_symbol_is_exported():
+    """Every function declared in include/*.h is exported by libflatgfa.so and bound."""
+    lib = pb.lib()
+    declared = set()
+    for h in ("fgfa_depth.h", "flatgfa.h"):
+        text = open(os.path.join(ROOT, "include", h), encoding="utf-8").read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b((?:fgfa|flatgfa)_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert declared == set(binding.EXPORTS), declared ^ set(binding.EXPORTS)
+
+
+def test_no_gpu_means_loud_failure():
+    if pb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pb.DepthError) as e:
+        pb.seg_depth_with_uniq_steps(np.array([0, 2], np.uint32), [0], [2], 2)
+    assert e.value.code == binding.FGFA_ERR_NO_DEVICE
+
+
+def test_ex1_image_matches_hand_derived_layout(tmp_path, fgfa_bin):
+    """byte layout of tests/depth/basic/ex1.gfa as a .flatgfa file."""
+    out = tmp_path / "ex1.flatgfa"
+    subprocess.run([fgfa_bin, "-I", os.path.join(GOLD, "ref_ex1.gfa"), "-o", str(out)], check=True)
+    img = out.read_bytes()
+    assert len(img) == 329
+    assert struct.unpack_from("<Q", img, 0)[0] == 0xB1011054
+    sizes = struct.unpack_from("<22Q", img, 8)
+    assert sizes == (8, 8, 2, 2, 1, 1, 2, 2, 3, 3, 2, 2, 0, 0, 2, 2, 5, 5, 0, 0, 6, 6)
+    assert img[184:192] == b"VN:Z:1.0"
+    assert struct.unpack_from("<QIIII", img, 192) == (1, 0, 1, 0, 0)
+    assert struct.unpack_from("<QIIII", img, 216) == (2, 1, 2, 0, 0)
+    assert struct.unpack_from("<6I", img, 240) == (0, 5, 0, 3, 0, 0)
+    assert struct.unpack_from("<4I", img, 264) == (0, 2, 0, 1)
+    assert struct.unpack_from("<4I", img, 280) == (2, 2, 1, 2)
+    assert img[296:308] == bytes.fromhex("000000000200000002000000")
+    assert img[308:310] == b"AC"
+    assert img[310:318] == bytes(8)
+    assert img[318:323] == b"path1"
+    assert img[323:329] == bytes([0, 1, 3, 1, 3, 2])
+
+
+def test_stdin_and_file_parsers_agree(tmp_path, fgfa_bin, golden):
+    for c in golden[:8]:
+        src = os.path.join(c["dir"], c["gfa"])
+        a, b = tmp_path / "a.flatgfa", tmp_path / "b.flatgfa"
+        subprocess.run([fgfa_bin, "-I", src, "-o", str(a)], check=True)
+        with open(src, "rb") as f:
+            subprocess.run([fgfa_bin, "-o", str(b)], stdin=f, check=True)
+        ia, ib = a.read_bytes(), b.read_bytes()
+        # parse_stream unwinds links before paths, parse_mem in file order (parse.rs:61-70
+        # vs 110-123): the depth-relevant pools (segs, paths' steps spans, steps) are identical.
+        ra, rb = O.file_depth(ia), O.file_depth(ib)
+        assert ra[0] == 0 and rb[0] == 0
+        for x, y in zip(ra[1:], rb[1:]):
+            assert (x == y).all()
+
+
+def test_product_parser_plus_oracle_reproduce_goldens(tmp_path, fgfa_bin, golden):
+    """GFA text -> (product parser, product writer) -> .flatgfa -> oracle == slow_odgi."""
+    for c in golden:
+        out = tmp_path / (c["name"] + ".flatgfa")
+        subprocess.run([fgfa_bin, "-I", os.path.join(c["dir"], c["gfa"]), "-o", str(out)], check=True)
+        rc, names, d, u = O.file_depth(out.read_bytes())
+        assert rc == 0
+        with open(os.path.join(c["dir"], c["depth"]), "rb") as f:
+            assert O.emit(names, d, u) == f.read(), c["name"]
+
+
+def test_parse_mem_drops_unterminated_last_line(tmp_path):
+    """memfile.rs:54-61: MemchrSplit yields nothing after the last newline."""
+    p = tmp_path / "g.gfa"
+    p.write_bytes(b"S\t1\tA\nS\t2\tC\nP\tx\t1+,2+\t*\nP\ty\t2+,2-\t*")   # no trailing newline
+    with pb.FlatGFA.parse(str(p)) as g:
+        assert (g.segment_count, g.path_count) == (2, 1)
+
+
+def test_parse_stream_keeps_unterminated_last_line(tmp_path, fgfa_bin):
+    out = tmp_path / "g.flatgfa"
+    subprocess.run([fgfa_bin, "-o", str(out)], input=b"S\t1\tA\nS\t2\tC\nP\tx\t1+,2+\t*\nP\ty\t2+,2-\t*", check=True)
+    with pb.FlatGFA.load(str(out)) as g:
+        assert (g.segment_count, g.path_count) == (2, 2)
+        assert g.step(1, 1) == (1, False)
+
+
+def test_accessors_match_flatgfa_c_semantics():
+    """flatgfa-c/src/lib.rs:79-172 on the reference's tiny.gfa (steps incl. `4-`)."""
+    with pb.FlatGFA.parse(os.path.join(GOLD, "ref_tiny.gfa")) as g:
+        assert g.segment_count == 4 and g.path_count == 2
+        assert g.path_name(0) == b"one" and g.path_name(1) == b"two" and g.path_name(2) is None
+        assert g.path_step_count(0) == 3 and g.path_step_count(1) == 4
+        assert g.path_step_count(2) == 0xFFFFFFFF                      # lib.rs:133-134
+        assert [g.step(0, i) for i in range(4)] == [(0, True), (1, True), (3, False), None]
+        assert g.step(7, 0) is None
+        assert g.seq(0) == b"CAAATAAG" and g.seq(3) == b"CCAACTCTCTG" and g.seq(4) is None
+
+
+def test_non_sequential_names_use_the_name_table(tmp_path):
+    p = tmp_path / "g.gfa"
+    p.write_bytes(b"S\t7\tA\nS\t3\tC\nS\t1\tG\nP\tx\t1+,7-,3+\t*\n")
+    with pb.FlatGFA.parse(str(p)) as g:
+        assert [g.step(0, i) for i in range(3)] == [(2, True), (0, False), (1, True)]
+
+
+def test_malformed_inputs_return_null_not_abort(tmp_path):
+    bad = {
+        "unknown_seg": b"S\t1\tA\nP\tx\t1+,9+\t*\n",
+        "no_tab": b"S 1 A\n",
+        "bad_kind": b"X\t1\n",
+        "empty_line": b"S\t1\tA\n\nS\t2\tC\n",
+        "bad_steps": b"S\t1\tA\nP\tx\t1+;1+\t*\n",
+        "long_cigar": b"S\t1\tA\nL\t1\t+\t1\t+\t300M\n",
+    }
+    for name, data in bad.items():
+        p = tmp_path / (name + ".gfa")
+        p.write_bytes(data)
+        with pytest.raises(pb.DepthError):
+            pb.FlatGFA.parse(str(p))
+    with pytest.raises(pb.DepthError):
+        pb.FlatGFA.parse(str(tmp_path / "does_not_exist.gfa"))
+
+
+def test_steps_parser_quirks_match_gfaline(tmp_path):
+    """gfaline.rs:230-263: a trailing segment number without orientation is dropped; one
+    stray byte after an orientation is swallowed (the state machine consumes it)."""
+    p = tmp_path / "g.gfa"
+    p.write_bytes(b"S\t1\tA\nS\t2\tC\nP\tx\t1+,2\t*\nP\ty\t2-x\t*\n")
+    with pb.FlatGFA.parse(str(p)) as g:
+        assert g.path_step_count(0) == 1 and g.path_step_count(1) == 1
+        assert g.step(1, 0) == (1, False)
+
+
+def test_view_errors(tmp_path):
+    img = flatgfa_io.build_image(np.array([0, 2, 2], np.uint32), [0], [3], 2)
+    n = C.c_uint64()
+    lib = pb.lib()
+    assert lib.fgfa_flatgfa_counts(img.ctypes.data, img.size, C.byref(n), None, None) == 0 and n.value == 2
+    bad = img.copy()
+    bad[0] ^= 0xFF
+    assert lib.fgfa_flatgfa_counts(bad.ctypes.data, bad.size, None, None, None) == binding.FGFA_ERR_BAD_MAGIC
+    assert lib.fgfa_flatgfa_counts(img.ctypes.data, img.size - 1, None, None, None) == binding.FGFA_ERR_TRUNCATED
+    assert lib.fgfa_flatgfa_counts(img.ctypes.data, 100, None, None, None) == binding.FGFA_ERR_TRUNCATED
+    for path, code in ((tmp_path / "bad.flatgfa", bad), ):
+        code.tofile(str(path))
+        with pytest.raises(pb.DepthError):
+            pb.FlatGFA.load(str(path))
+
+
+def test_capacity_slack_is_skipped(tmp_path):
+    """file.rs:163-167: each pool occupies capacity (not len) elements."""
+    cfg = synth.CONFIGS["tiny"]
+    steps, s, e = synth.make_graph(cfg)
+    tight = flatgfa_io.build_image(steps, s, e, cfg.n_segs)
+    slack = flatgfa_io.build_image(steps, s, e, cfg.n_segs, slack=5)
+    assert slack.size > tight.size
+    a, b = O.file_depth(tight.tobytes()), O.file_depth(slack.tobytes())
+    assert a[0] == 0 and b[0] == 0
+    for x, y in zip(a[1:], b[1:]):
+        assert (x == y).all()
+    p = tmp_path / "slack.flatgfa"
+    slack.tofile(str(p))
+    with pb.FlatGFA.load(str(p)) as g:
+        assert g.segment_count == cfg.n_segs and g.path_count == cfg.n_paths
+        assert g.path_step_count(3) == int(e[3] - s[3])
+        assert g.step(2, 5) == (int(steps[s[2] + 5] >> 1), not bool(steps[s[2] + 5] & 1))
+
+
+def test_dump_round_trip(tmp_path):
+    src = os.path.join(GOLD, "rand_05.gfa")
+    with pb.FlatGFA.parse(src) as g:
+        g.dump(str(tmp_path / "a.flatgfa"))
+        with pb.FlatGFA.load(str(tmp_path / "a.flatgfa")) as h:
+            assert (h.segment_count, h.path_count) == (g.segment_count, g.path_count)
+            for p in range(g.path_count):
+                assert h.path_name(p) == g.path_name(p)
+                n = g.path_step_count(p)
+                assert h.path_step_count(p) == n
+                assert [h.step(p, i) for i in range(n)] == [g.step(p, i) for i in range(n)]
+            h.dump(str(tmp_path / "b.flatgfa"))
+    assert (tmp_path / "a.flatgfa").read_bytes() == (tmp_path / "b.flatgfa").read_bytes()
+
+
+def test_cli_rejects_out_of_scope(fgfa_bin):
+    r = subprocess.run([fgfa_bin, "-I", os.path.join(GOLD, "ref_ex1.gfa"), "chop", "-c", "3"], capture_output=True)
+    assert r.returncode != 0 and b"scope" in r.stderr
+
+
+def test_synth_is_deterministic_and_shaped():
+    cfg = synth.CONFIGS["tinyE"]
+    a = synth.make_graph(cfg)
+    b = synth.make_graph(cfg)
+    assert all((x == y).all() for x, y in zip(a, b))
+    steps, s, e = a
+    assert int(e[-1]) == cfg.n_steps and int(s[0]) == 0 and (s[1:] == e[:-1]).all()
+    assert int((steps >> 1).max()) < cfg.n_segs
+    rc, d, u = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+    assert rc == 0 and int(d.sum()) == cfg.n_steps
+    assert int(d.max()) > 50            # the hot windows really are hot
+    assert (u <= np.minimum(d, cfg.n_paths)).all()
