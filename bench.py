@@ -1,0 +1,302 @@
+#!/usr/bin/env python3
+"""Benchmark of the node-depth hot path (`fgfa depth -d`: depth + depth.uniq).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C|B|E] [--impl ours|reference]
+
+One process per GPU (under torchrun for N > 1).  A "step" is one full pass of the hot
+path over the synthetic graph: zero the outputs, kernel A (step stream), kernel B
+(seen-bitmap popcount) and, for N > 1, the allreduce of [depth | uniq].  The workload is
+BASELINE.json configs[2] (the 400M-step graph the metric is quoted on); at N > 1 the SAME
+graph is sharded by whole paths (configs[3]), so scaling is "strong".
+
+`value`     steps/s with the shard resident in HBM (CUDA events, max over ranks).
+`e2e`       the same metric through the host-buffer entry point: pinned host steps ->
+            H2D -> kernels (-> allreduce) -> D2H of depth/uniq, every step.
+`roofline`  algorithmic bytes of kernel A / its CUDA-event duration inside the timed
+            region, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`cpu_baseline`  the oracle (C port of depth.rs:15-39, single thread like the reference)
+            timed on this box, rank 0, N = 1 only.
+`--impl reference` times that CPU port alone (the Rust reference cannot be built here).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "path steps/sec for fgfa depth (depth + depth.uniq)"
+UNIT = "steps/s"
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().split("\n"):
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) >= 8:
+                        self.rows.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def time_oracle(cfg, steps, start, end, reps):
+    """Oracle (kind "port") on the full workload: returns best steps/s over `reps`."""
+    import oracle_lib as O
+    best = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc, d, u = O.depth_with_uniq(steps, start, end, cfg.n_segs)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        best = max(best, cfg.n_steps / dt)
+    return best
+
+
+def run_reference(args, cfg, rank):
+    """--impl reference: the reference's algorithm on the host CPU.  The Rust crate cannot
+    be built here (no cargo, crates not vendored), so this is the oracle port of
+    flatgfa/src/ops/depth.rs:15-39; like the reference loop it is single-threaded."""
+    if rank != 0:
+        return
+    from pollen_b200 import synth
+    steps, start, end = synth.make_graph(cfg)
+    import oracle_lib as O
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rc, d, u = O.depth_with_uniq(steps, start, end, cfg.n_segs)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    v = cfg.n_steps * len(times) / total
+    sample = f"full config {cfg.name} ({cfg.n_steps} steps) per step, {len(times)} timed passes"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": workload_config(cfg, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(cfg, n_gpus):
+    return {
+        "workload": f"{cfg.name}: {cfg.description}",
+        "n_segs": cfg.n_segs, "n_paths": cfg.n_paths, "n_steps": cfg.n_steps,
+        "generator": "haplotype walk (SURVEY.md 8d), seed 0xB1011054" if cfg.kind == 0 else "see pollen_b200/csrc/synth.cpp",
+        "sharding": "single GPU" if n_gpus == 1 else f"whole paths LPT-partitioned over {n_gpus} GPUs + allreduce of [depth|uniq]",
+        "l2_policy": "inputs larger than L2 (per-GPU steps shard >= 200 MB vs 126 MB L2); no explicit flush",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+
+    from pollen_b200 import synth
+    cfg = synth.CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pollen_b200 as pb
+    from pollen_b200 import sharding
+
+    if not torch.cuda.is_available() or pb.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    # ---- this rank's shard of the graph ------------------------------------------------
+    start, end = synth.make_spans(cfg.n_paths, cfg.n_steps, cfg.jitter_pct)
+    parts = sharding.lpt_partition(end - start, world)
+    my_paths = parts[rank]
+    if world == 1:
+        h_steps_np, ls, le = synth.make_graph(cfg)
+    else:
+        h_steps_np, ls, le = synth.make_graph(cfg, path_subset=my_paths)
+    n_local = int(h_steps_np.size)
+    h_steps = torch.from_numpy(h_steps_np.view(np.int32)).pin_memory()      # pinned host copy for e2e
+    d_steps = torch.empty(n_local, dtype=torch.int32, device=dev)
+    d_steps.copy_(h_steps)
+    eng = sharding.ShardedDepth(ls, le, cfg.n_segs, dev)
+    stream = torch.cuda.current_stream(dev)
+    launches_per_step = eng.plan.launches(True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident throughput ----------------------------------------------------
+    for _ in range(args.warmup):
+        eng.run(d_steps, stream)
+    eng.status()
+    probes = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for a, b in probes:            # torch creates the CUDA event lazily, on first record
+        a.record(stream)
+        b.record(stream)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    ev0.record(stream)
+    for k in range(args.steps):
+        eng.plan.set_probe(probes[k][0].cuda_event, probes[k][1].cuda_event)
+        eng.run(d_steps, stream)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    eng.status()
+    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    ms_kernel = torch.tensor([statistics.mean(a.elapsed_time(b) for a, b in probes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_kernel, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms_total.item()) / args.steps
+    value = cfg.n_steps / (ms_per_step * 1e-3)
+
+    # checksum of the result (sum of depth must equal the number of steps)
+    depth_sum = int(eng.depth.to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
+    assert depth_sum == cfg.n_steps, (depth_sum, cfg.n_steps)
+
+    # ---- roofline of the dominant kernel (kernel A, the step stream) -------------------
+    peak, peak_src = peak_hbm()
+    alg_bytes = 4.0 * n_local + 8.0 * len(my_paths) + 4.0 * cfg.n_segs   # per launch, this rank (slowest rank's time)
+    k_ms = float(ms_kernel.item())
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_step_stream_merged", "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "whole_step_frac": (4.0 * cfg.n_steps + 8.0 * cfg.n_paths + 8.0 * cfg.n_segs) / world / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    # ---- end to end: host buffers in, host results out ---------------------------------
+    e2e_steps = max(1, args.e2e_steps)
+    if world == 1:
+        # the drop-in C-ABI call on host buffers (allocates, uploads in pipelined groups,
+        # runs, downloads, widens to u64) -- what a caller of the reference's op would use
+        lib = pb.lib()
+        d64 = np.empty(cfg.n_segs, np.uint64)
+        u64 = np.empty(cfg.n_segs, np.uint64)
+        s32, e32 = np.ascontiguousarray(ls, np.uint32), np.ascontiguousarray(le, np.uint32)
+
+        def e2e_once():
+            rc = lib.fgfa_seg_depth_with_uniq_steps(h_steps.data_ptr(), n_local, s32.ctypes.data, e32.ctypes.data,
+                                                    len(s32), cfg.n_segs, d64.ctypes.data, u64.ctypes.data)
+            assert rc == 0, rc
+        e2e_once()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_once()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        assert int(d64.sum()) == cfg.n_steps
+        e2e_api = "fgfa_seg_depth_with_uniq_steps (C ABI, pinned host steps)"
+    else:
+        out_host = torch.empty(2 * cfg.n_segs, dtype=torch.int32).pin_memory()
+
+        def e2e_once():
+            d_steps.copy_(h_steps, non_blocking=True)
+            eng.run(d_steps, stream)
+            out_host.copy_(eng.out, non_blocking=True)
+            stream.synchronize()
+        e2e_once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_once()
+        barrier()
+        e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_s = float(e2e_t.item())
+        e2e_api = "ShardedDepth.run on pinned host shards (H2D + kernels + NCCL allreduce + D2H)"
+    e2e = {"value": cfg.n_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local + 8 * len(my_paths),
+           "d2h_bytes_per_step": 8 * cfg.n_segs, "ms_per_step": e2e_s * 1e3, "api": e2e_api, "steps": e2e_steps}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        v = time_oracle(cfg, h_steps_np, ls, le, reps=3)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"full config {cfg.name} ({cfg.n_steps} steps), best of 3 passes of the single-threaded oracle",
+               "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(cfg, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,312 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libflatgfa.so), against
+the golden vectors and the oracle.  Bit-exact: this is integer work."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import pollen_b200 as pb
+from pollen_b200 import binding, flatgfa_io, sharding, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _read(case, key):
+    with open(os.path.join(case["dir"], case[key]), "rb") as f:
+        return f.read()
+
+
+def _check_vs_oracle(steps, start, end, n_segs):
+    rc, od, ou = O.depth_with_uniq(steps, start, end, n_segs)
+    assert rc == 0
+    gd, gu = pb.seg_depth_with_uniq_steps(steps, start, end, n_segs)
+    assert (gd == od).all() and (gu == ou).all()
+    assert (pb.seg_depth_steps(steps, start, end, n_segs) == od).all()
+    return od, ou
+
+
+# ---------------------------------------------------------------- golden vectors ----
+def test_goldens_through_flatgfa_c_abi(golden):
+    """flatgfa_parse -> flatgfa_seg_depth -> flatgfa_format_seg_depth == slow_odgi output."""
+    for c in golden:
+        with pb.FlatGFA.parse(os.path.join(c["dir"], c["gfa"])) as g:
+            d, u = pb.seg_depth_with_uniq(g)
+            assert pb.SegDepth(g, d, u).emit() == _read(c, "depth"), c["name"]
+            assert (pb.seg_depth(g) == d).all()
+
+
+def test_goldens_through_cli(golden, fgfa_bin, tmp_path):
+    """`fgfa -I x.gfa depth -d` (tests/turnt.toml:179-181), stdin, and `-i x.flatgfa`."""
+    for c in golden:
+        src = os.path.join(c["dir"], c["gfa"])
+        want = _read(c, "depth")
+        assert subprocess.run([fgfa_bin, "-I", src, "depth", "-d"], capture_output=True, check=True).stdout == want
+        with open(src, "rb") as f:
+            assert subprocess.run([fgfa_bin, "depth", "--graph-depth-table"], stdin=f, capture_output=True, check=True).stdout == want
+        flat = tmp_path / (c["name"] + ".flatgfa")
+        subprocess.run([fgfa_bin, "-I", src, "-o", str(flat)], check=True)
+        assert subprocess.run([fgfa_bin, "-i", str(flat), "depth", "-d"], capture_output=True, check=True).stdout == want
+
+
+def test_golden_path_subsets_via_span_table(golden):
+    """odgi/slow_odgi's `-s/--paths` subset == running the op on a subset of spans."""
+    for c in golden:
+        if "subset_paths" not in c:
+            continue
+        names, steps, start, end, pnames = O.read_gfa(_read(c, "gfa").decode())
+        keep = [i for i, n in enumerate(pnames) if n in c["subset_paths"]]
+        d, u = pb.seg_depth_with_uniq_steps(steps, start[keep], end[keep], len(names))
+        assert O.emit(names, d, u) == _read(c, "subset_depth"), c["name"]
+
+
+# ------------------------------------------------------------- oracle, seeded -------
+@pytest.mark.parametrize("name", ["tiny", "tinyE", "B"])
+def test_synthetic_vs_oracle(name):
+    cfg = synth.CONFIGS[name]
+    steps, s, e = synth.make_graph(cfg)
+    d, u = _check_vs_oracle(steps, s, e, cfg.n_segs)
+    assert int(d.sum()) == cfg.n_steps
+
+
+def test_uniform_random_ids_vs_oracle():
+    cfg = synth.Config("u", 70_001, 11, 2_000_003, synth.KIND_UNIFORM, 40, "")
+    steps, s, e = synth.make_graph(cfg)
+    _check_vs_oracle(steps, s, e, cfg.n_segs)
+
+
+def test_image_entry_points_and_misaligned_steps_pool(tmp_path):
+    """.flatgfa images whose steps pool starts at byte offsets 0..3 mod 4 (odd header
+    lengths) and with capacity > len (file.rs:163-167)."""
+    cfg = synth.CONFIGS["tiny"]
+    steps, s, e = synth.make_graph(cfg)
+    rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+    lib = pb.lib()
+    for hdr, slack in ((b"VN:Z:1.0", 0), (b"VN:Z:1.0x", 0), (b"VN:Z:1.0xy", 3), (b"VN:Z:1.0xyz", 1), (b"", 2)):
+        img = flatgfa_io.build_image(steps, s, e, cfg.n_segs, header=hdr, slack=slack)
+        d = np.empty(cfg.n_segs, np.uint64)
+        u = np.empty(cfg.n_segs, np.uint64)
+        assert lib.fgfa_seg_depth_with_uniq(img.ctypes.data, img.size, d.ctypes.data, u.ctypes.data) == 0
+        assert (d == od).all() and (u == ou).all()
+        d2 = np.empty(cfg.n_segs, np.uint64)
+        assert lib.fgfa_seg_depth(img.ctypes.data, img.size, d2.ctypes.data) == 0 and (d2 == od).all()
+        rc2, names, fd, fu = O.file_depth(img.tobytes())
+        assert rc2 == 0 and (fd == od).all() and (fu == ou).all()
+    p = tmp_path / "t.flatgfa"
+    img.tofile(str(p))
+    with pb.FlatGFA.load(str(p)) as g:
+        d, u = g.seg_depth_with_uniq()
+        assert (d == od).all() and (u == ou).all()
+        assert pb.SegDepth(g, d, u).emit() == O.emit(names, od, ou)
+
+
+# ------------------------------------------------------------------- edge cases -----
+def test_empty_and_degenerate_graphs():
+    z = np.zeros(0, np.uint32)
+    d, u = pb.seg_depth_with_uniq_steps(z, [], [], 0)
+    assert d.size == 0 and u.size == 0
+    d, u = pb.seg_depth_with_uniq_steps(z, [], [], 37)            # segments but no paths
+    assert not d.any() and not u.any()
+    d, u = pb.seg_depth_with_uniq_steps(z, [0, 0, 0], [0, 0, 0], 5)  # only empty paths
+    assert not d.any() and not u.any()
+    one = np.array([(4 << 1) | 1], np.uint32)
+    d, u = pb.seg_depth_with_uniq_steps(one, [0], [1], 5)
+    assert d.tolist() == [0, 0, 0, 0, 1] and u.tolist() == [0, 0, 0, 0, 1]
+    loop = np.full(10_000, 2 << 1, np.uint32)                     # one path, one segment, 10k times
+    d, u = pb.seg_depth_with_uniq_steps(loop, [0], [10_000], 3)
+    assert d.tolist() == [0, 0, 10_000] and u.tolist() == [0, 0, 1]
+
+
+def test_ragged_spans_every_alignment_and_length():
+    """Path starts at every offset mod 4, lengths around the 4096-step chunk size, empty
+    paths in between, n_segs not a multiple of 32."""
+    rng = np.random.default_rng(11)
+    lens = [0, 1, 2, 3, 4, 5, 4095, 4096, 4097, 0, 8191, 8193, 12288, 7, 0, 4093, 1, 16385]
+    end = np.cumsum(lens).astype(np.uint32)
+    start = (end - np.array(lens)).astype(np.uint32)
+    n_segs = 1021
+    steps = rng.integers(0, 2 * n_segs, int(end[-1]), dtype=np.uint32)
+    _check_vs_oracle(steps, start, end, n_segs)
+    # same spans, shifted by 1..3 elements inside a larger pool
+    for shift in (1, 2, 3):
+        pool = np.concatenate([rng.integers(0, 2 * n_segs, shift, dtype=np.uint32), steps,
+                               rng.integers(0, 2 * n_segs, 5, dtype=np.uint32)])
+        _check_vs_oracle(pool, start + shift, end + shift, n_segs)
+
+
+def test_overlapping_and_unordered_spans():
+    """The reference honours arbitrary spans (pool.rs:341-347); so must the kernels."""
+    rng = np.random.default_rng(5)
+    n_segs = 333
+    steps = rng.integers(0, 2 * n_segs, 50_000, dtype=np.uint32)
+    start = np.array([40_000, 0, 10_000, 10_000, 49_999, 123], np.uint32)
+    end = np.array([50_000, 30_000, 20_000, 10_000, 50_000, 4567], np.uint32)
+    _check_vs_oracle(steps, start, end, n_segs)
+
+
+def test_errors_where_the_reference_panics():
+    steps = np.array([0, 2, 8, 6], np.uint32)
+    with pytest.raises(pb.DepthError) as e:
+        pb.seg_depth_with_uniq_steps(steps, [0], [4], 4)          # segment 4 >= n_segs (depth.rs:29)
+    assert e.value.code == binding.FGFA_ERR_SEG_OOB
+    with pytest.raises(pb.DepthError) as e:
+        pb.seg_depth_steps(steps, [0], [4], 4)
+    assert e.value.code == binding.FGFA_ERR_SEG_OOB
+    with pytest.raises(pb.DepthError) as e:
+        pb.seg_depth_with_uniq_steps(steps, [0], [5], 9)          # span past the pool (pool.rs:341-347)
+    assert e.value.code == binding.FGFA_ERR_SPAN_OOB
+    with pytest.raises(pb.DepthError) as e:
+        pb.seg_depth_with_uniq_steps(steps, [3], [2], 9)
+    assert e.value.code == binding.FGFA_ERR_SPAN_OOB
+    # a bad step buried in a full interior chunk
+    big = np.zeros(50_000, np.uint32)
+    big[20_000] = 2 * 7
+    with pytest.raises(pb.DepthError) as e:
+        pb.seg_depth_with_uniq_steps(big, [0], [50_000], 7)
+    assert e.value.code == binding.FGFA_ERR_SEG_OOB
+    # and the engine is still usable afterwards
+    d, u = pb.seg_depth_with_uniq_steps(steps, [0], [4], 5)
+    assert d.tolist() == [1, 1, 0, 1, 1]
+
+
+# --------------------------------------------------------- device-resident plan -----
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def test_plan_reuse_batches_and_feed_pipeline(torch_cuda):
+    torch = torch_cuda
+    cfg = synth.CONFIGS["tinyE"]
+    steps, s, e = synth.make_graph(cfg)
+    rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+    d_steps = _dev(torch, steps)
+    st = torch.cuda.current_stream().cuda_stream
+    row_bytes = ((cfg.n_segs + 31) // 32 + 31) // 32 * 32 * 4
+    for budget, batches in ((0, 1), (row_bytes, 5), (2 * row_bytes + 8, 3)):
+        plan = pb.DepthPlan(s, e, cfg.n_segs, cfg.n_steps, bitmap_budget_bytes=budget)
+        depth = torch.full((cfg.n_segs,), -1, dtype=torch.int32, device="cuda")
+        uniq = torch.full((cfg.n_segs,), -1, dtype=torch.int32, device="cuda")
+        for _ in range(3):                                        # re-runs must see a clean bitmap
+            plan.run(d_steps, depth, uniq, st)
+            plan.status(st)
+            assert (depth.cpu().numpy().view(np.uint32) == od).all()
+            assert (uniq.cpu().numpy().view(np.uint32) == ou).all()
+        # piecewise feed
+        depth.fill_(-1)
+        uniq.fill_(-1)
+        plan.begin(depth, st)
+        for lo, hi in ((0, 1), (1, 1), (1, 4), (4, 5)):
+            plan.feed(d_steps, lo, hi, depth, uniq, st)
+        plan.finish(uniq, st)
+        plan.status(st)
+        assert (depth.cpu().numpy().view(np.uint32) == od).all()
+        assert (uniq.cpu().numpy().view(np.uint32) == ou).all()
+        # depth only
+        depth.fill_(-1)
+        plan.run(d_steps, depth, None, st)
+        plan.status(st)
+        assert (depth.cpu().numpy().view(np.uint32) == od).all()
+        assert plan.launches(True) == 2 * batches and plan.launches(False) == batches
+        plan.close()
+
+
+def test_misaligned_device_pointer_and_one_shot_device_abi(torch_cuda):
+    torch = torch_cuda
+    cfg = synth.CONFIGS["tiny"]
+    steps, s, e = synth.make_graph(cfg)
+    rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+    lib = pb.lib()
+    for shift in (0, 1, 2, 3):
+        padded = np.concatenate([np.full(shift, 0xFFFFFFFF, np.uint32), steps])
+        d_all = _dev(torch, padded)
+        d_steps = d_all[shift:]
+        assert (d_steps.data_ptr() // 4) % 4 == shift
+        depth = torch.empty(cfg.n_segs, dtype=torch.int32, device="cuda")
+        uniq = torch.empty(cfg.n_segs, dtype=torch.int32, device="cuda")
+        d_s, d_e = _dev(torch, s), _dev(torch, e)
+        torch.cuda.synchronize()
+        rc = lib.fgfa_depth_device(d_steps.data_ptr(), cfg.n_steps, d_s.data_ptr(), d_e.data_ptr(),
+                                   cfg.n_paths, cfg.n_segs, depth.data_ptr(), uniq.data_ptr(), None)
+        assert rc == 0
+        assert (depth.cpu().numpy().view(np.uint32) == od).all()
+        assert (uniq.cpu().numpy().view(np.uint32) == ou).all()
+
+
+def test_sharded_partials_sum_to_the_whole(torch_cuda):
+    """Whole-path shards are exactly additive (depth.rs:25-35): what the allreduce relies on."""
+    torch = torch_cuda
+    cfg = synth.CONFIGS["B"]
+    steps, s, e = synth.make_graph(cfg)
+    rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+    parts = sharding.lpt_partition(e - s, 4)
+    total = np.zeros(2 * cfg.n_segs, np.uint32)
+    for part in parts:
+        ls_steps, ls, le = synth.make_graph(cfg, path_subset=part)
+        eng = sharding.ShardedDepth(ls, le, cfg.n_segs, torch.device("cuda:0"))
+        eng.run(_dev(torch, ls_steps))
+        eng.status()
+        total += eng.out.cpu().numpy().view(np.uint32)
+    assert (total[: cfg.n_segs] == od).all() and (total[cfg.n_segs:] == ou).all()
+
+
+# ------------------------------------------------------------------- full size ------
+def test_full_size_config_C_vs_oracle_and_properties(torch_cuda):
+    """BASELINE.json configs[2]: 5M segments, 90 paths, 400M steps (device-resident)."""
+    torch = torch_cuda
+    cfg = synth.CONFIGS["C"]
+    steps, s, e = synth.make_graph(cfg)
+    d_steps = _dev(torch, steps)
+    plan = pb.DepthPlan(s, e, cfg.n_segs, cfg.n_steps)
+    depth = torch.empty(cfg.n_segs, dtype=torch.int32, device="cuda")
+    uniq = torch.empty(cfg.n_segs, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    plan.run(d_steps, depth, uniq, st)
+    plan.status(st)
+    gd = depth.cpu().numpy().view(np.uint32)
+    gu = uniq.cpu().numpy().view(np.uint32)
+    # size-independent properties
+    assert int(gd.sum(dtype=np.uint64)) == cfg.n_steps
+    assert (gu <= np.minimum(gd, cfg.n_paths)).all() and ((gu > 0) == (gd > 0)).all()
+    # path-additivity: first 30 paths + remaining 60 paths == all 90
+    acc_d = np.zeros(cfg.n_segs, np.uint64)
+    acc_u = np.zeros(cfg.n_segs, np.uint64)
+    for lo, hi in ((0, 30), (30, 90)):
+        sub = pb.DepthPlan(s[lo:hi], e[lo:hi], cfg.n_segs, cfg.n_steps)
+        sub.run(d_steps, depth, uniq, st)
+        sub.status(st)
+        acc_d += depth.cpu().numpy().view(np.uint32)
+        acc_u += uniq.cpu().numpy().view(np.uint32)
+        sub.close()
+    assert (acc_d == gd).all() and (acc_u == gu).all()
+    # and the oracle itself (about 1.5 s of CPU at this size)
+    rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+    assert rc == 0 and (gd == od).all() and (gu == ou).all()
+
+
+def test_full_size_config_E_skewed_vs_oracle(torch_cuda):
+    """BASELINE.json configs[4] shape: 8 long looping paths with hot segments."""
+    torch = torch_cuda
+    cfg = synth.CONFIGS["E"]
+    steps, s, e = synth.make_graph(cfg)
+    d_steps = _dev(torch, steps)
+    plan = pb.DepthPlan(s, e, cfg.n_segs, cfg.n_steps)
+    out = torch.empty(2 * cfg.n_segs, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    plan.run(d_steps, out[: cfg.n_segs], out[cfg.n_segs:], st)
+    plan.status(st)
+    g = out.cpu().numpy().view(np.uint32)
+    rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+    assert rc == 0 and (g[: cfg.n_segs] == od).all() and (g[cfg.n_segs:] == ou).all()
+    assert int(od.max()) > 10_000                                  # hot segments are hot
