@@ -113,6 +113,11 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
                                    uint32_t n_paths, uint32_t n_segs, uint64_t* depth_out,
                                    uint64_t* uniq_out);
 
+/* The host-buffer entry points keep their device/pinned staging and the last plan in a
+ * process-wide workspace between calls; this frees it (it is re-created on demand).
+ * Setting FGFA_WORKSPACE=0 in the environment frees it after every call instead. */
+void fgfa_release_workspace(void);
+
 /* seg_depth_with_uniq / seg_depth over a .flatgfa image in host memory (e.g. the mmap
  * the reference's `file::view` takes, file.rs:185-213).  Outputs: n_segs u64 each,
  * where n_segs is what fgfa_flatgfa_counts() reports. */

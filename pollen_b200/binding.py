@@ -78,6 +78,7 @@ EXPORTS = {
     "fgfa_depth_plan_scratch_bytes": (C.c_size_t, [C.c_void_p]),
     "fgfa_depth_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_seg_depth_with_uniq_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fgfa_release_workspace": (None, []),
     "fgfa_flatgfa_counts": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fgfa_seg_depth_with_uniq": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "fgfa_seg_depth": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -39,7 +39,10 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 constexpr size_t kDefaultBitmapBudget = 64ull << 20;  // stays resident in the 126 MB L2
-constexpr int kBlocksPerSM = 6;
+// Register cap / grid multiple for kernel A.  Shared memory (2 x 16 KiB per CTA) limits
+// residency to 6 CTAs per SM; a grid of 8 CTAs per SM measured best on B200 (the extra
+// CTAs start as the first ones drain, which evens out the tail).
+constexpr int kBlocksPerSM = 8;
 
 }  // namespace
 
@@ -50,10 +53,9 @@ struct fgfa_depth_plan {
     int device = 0, sms = 0;
     uint32_t n_words = 0, words_per_row = 0, rows_per_batch = 0;
     uint32_t misalign = 0;                 // d_steps misalignment (elements) the tables are built for
-    uint32_t* d_start = nullptr;           // spans shifted by `misalign`
-    uint32_t* d_end = nullptr;
-    uint32_t* d_prefix = nullptr;          // chunk_prefix[n_paths+1]
-    std::vector<uint32_t> h_prefix;
+    fgfa::ChunkDesc* d_chunks = nullptr;   // chunk table (spans shifted by `misalign`)
+    size_t chunk_capacity = 0;
+    std::vector<uint32_t> h_prefix;        // chunks before path p, [n_paths+1]
     uint32_t* d_bitmap = nullptr;          // [rows_per_batch][words_per_row], zero between runs
     uint32_t* d_err = nullptr;
     size_t scratch_bytes = 0;
@@ -66,23 +68,30 @@ namespace {
 
 int build_tables(fgfa_depth_plan* pl, uint32_t misalign) {
     const uint32_t n = pl->n_paths;
-    std::vector<uint32_t> s(n), e(n);
     pl->h_prefix.assign((size_t)n + 1, 0u);
     uint64_t chunks = 0;
     for (uint32_t p = 0; p < n; ++p) {
         const uint64_t sp = (uint64_t)pl->h_start[p] + misalign, ep = (uint64_t)pl->h_end[p] + misalign;
         if (ep > 0xFFFFFFFFull) return fail(FGFA_ERR_TOO_LARGE, "steps pool too large for a misaligned device pointer");
-        s[p] = (uint32_t)sp;
-        e[p] = (uint32_t)ep;
         if (ep > sp) chunks += (ep - (sp & ~3ull) + fgfa::kChunk - 1) / fgfa::kChunk;
         if (chunks > 0xFFFFFFFFull) return fail(FGFA_ERR_TOO_LARGE, "too many chunks");
         pl->h_prefix[p + 1] = (uint32_t)chunks;
     }
-    if (n) {
-        CU(cudaMemcpy(pl->d_start, s.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(pl->d_end, e.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    std::vector<fgfa::ChunkDesc> table((size_t)chunks);
+    for (uint32_t p = 0; p < n; ++p) {
+        const uint32_t sp = pl->h_start[p] + misalign, ep = pl->h_end[p] + misalign;
+        uint64_t a = sp & ~3u;
+        for (uint32_t c = pl->h_prefix[p]; c < pl->h_prefix[p + 1]; ++c, a += fgfa::kChunk)
+            table[c] = fgfa::ChunkDesc{(uint32_t)a, sp, ep, p};
     }
-    CU(cudaMemcpy(pl->d_prefix, pl->h_prefix.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
+    if (chunks > pl->chunk_capacity) {
+        cudaFree(pl->d_chunks);
+        pl->d_chunks = nullptr;
+        CU(cudaMalloc(&pl->d_chunks, (size_t)chunks * sizeof(fgfa::ChunkDesc)));
+        pl->chunk_capacity = (size_t)chunks;
+    }
+    if (chunks)
+        CU(cudaMemcpy(pl->d_chunks, table.data(), (size_t)chunks * sizeof(fgfa::ChunkDesc), cudaMemcpyHostToDevice));
     pl->misalign = misalign;
     return FGFA_OK;
 }
@@ -94,12 +103,10 @@ int launch_stream(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     if (chunks == 0) return FGFA_OK;
     fgfa::StreamParams P{};
     P.steps = d_steps_aligned;
-    P.n_steps = pl->n_steps + pl->misalign;
-    P.span_start = pl->d_start;
-    P.span_end = pl->d_end;
-    P.chunk_prefix = pl->d_prefix;
+    P.chunks = pl->d_chunks;
+    P.chunk_lo = pl->h_prefix[lo];
+    P.chunk_hi = pl->h_prefix[hi];
     P.path_lo = lo;
-    P.path_hi = hi;
     P.n_segs = pl->n_segs;
     P.words_per_row = pl->words_per_row;
     P.depth = d_depth;
@@ -211,26 +218,24 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
     pl->rows_per_batch = (uint32_t)rows;
     const size_t bitmap_bytes = std::max<size_t>(row_bytes * rows, 4);
 #define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(cuda_fail(e_, #x)); } while (0)
-    CUB_(cudaMalloc(&pl->d_start, std::max<size_t>((size_t)n_paths * 4, 4)));
-    CUB_(cudaMalloc(&pl->d_end, std::max<size_t>((size_t)n_paths * 4, 4)));
-    CUB_(cudaMalloc(&pl->d_prefix, ((size_t)n_paths + 1) * 4));
     CUB_(cudaMalloc(&pl->d_bitmap, bitmap_bytes));
     CUB_(cudaMalloc(&pl->d_err, 4));
     CUB_(cudaMemset(pl->d_bitmap, 0, bitmap_bytes));
     CUB_(cudaMemset(pl->d_err, 0, 4));
 #undef CUB_
-    pl->scratch_bytes = bitmap_bytes + (size_t)n_paths * 12 + 8;
+    // kernel A wants 6 CTAs x 32 KiB of shared memory per SM: ask for the large carve-out
+    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     int rc = build_tables(pl, 0);
     if (rc) return bail(rc);
+    pl->scratch_bytes = bitmap_bytes + pl->chunk_capacity * sizeof(fgfa::ChunkDesc) + 4;
     *out = pl;
     return FGFA_OK;
 }
 
 void fgfa_depth_plan_destroy(fgfa_depth_plan_t* pl) {
     if (!pl) return;
-    cudaFree(pl->d_start);
-    cudaFree(pl->d_end);
-    cudaFree(pl->d_prefix);
+    cudaFree(pl->d_chunks);
     cudaFree(pl->d_bitmap);
     cudaFree(pl->d_err);
     delete pl;

@@ -14,9 +14,9 @@
 //
 // Work decomposition: a *chunk* is up to kChunk consecutive steps of ONE path
 // (a chunk never straddles two paths because the bitmap row depends on the path);
-// chunk c of path p starts at the 16-byte-aligned element (start_p & ~3) + c*kChunk
-// so that every 128-bit load is aligned even though a path's span start is only
-// 4-byte aligned.
+// chunk k of path p starts at the 16-byte-aligned element (start_p & ~3) + k*kChunk
+// so that every 128-bit copy is aligned even though a path's span start is only
+// 4-byte aligned.  The host builds the chunk table once per plan.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -27,18 +27,23 @@ constexpr int kThreads = 256;          // threads per CTA in kernel A
 constexpr int kItems = 16;             // steps per thread per chunk
 constexpr int kChunk = kThreads * kItems;  // 4096 steps = 16 KiB of the pool
 
+// One unit of work of kernel A: up to kChunk consecutive steps of one path.
+struct __align__(16) ChunkDesc {
+    uint32_t a;      // first element of the chunk (16-byte aligned relative to `steps`)
+    uint32_t s, e;   // the owning path's span [s, e) in the steps pool
+    uint32_t path;   // path index (selects the seen-bitmap row)
+};
+
 struct StreamParams {
-    const uint32_t* __restrict__ steps;   // device: the steps pool (Handle words)
-    uint64_t n_steps;                     // pool length (for the tail guard)
-    const uint32_t* __restrict__ span_start;  // device [n_paths]
-    const uint32_t* __restrict__ span_end;    // device [n_paths]
-    const uint32_t* __restrict__ chunk_prefix;  // device [n_paths+1]: chunks before path p
-    uint32_t path_lo, path_hi;            // this launch covers paths [path_lo, path_hi)
+    const uint32_t* __restrict__ steps;       // device: the steps pool (Handle words), 16-byte aligned
+    const ChunkDesc* __restrict__ chunks;     // device: chunk table of the whole plan
+    uint32_t chunk_lo, chunk_hi;              // this launch covers chunks [chunk_lo, chunk_hi)
+    uint32_t path_lo;                         // path whose bitmap row is row 0 of `bitmap`
     uint32_t n_segs;
-    uint32_t words_per_row;               // bitmap row pitch in 32-bit words
-    uint32_t* __restrict__ depth;         // device [n_segs], pre-zeroed
-    uint32_t* __restrict__ bitmap;        // device [(path_hi-path_lo) rows][words_per_row], zero
-    uint32_t* __restrict__ err;           // sticky error flag (bit 0: segment id out of range)
+    uint32_t words_per_row;                   // bitmap row pitch in 32-bit words
+    uint32_t* __restrict__ depth;             // device [n_segs], pre-zeroed
+    uint32_t* __restrict__ bitmap;            // device [rows][words_per_row], zero on entry
+    uint32_t* __restrict__ err;               // sticky error flag (bit 0: segment id out of range)
 };
 
 // ---------------------------------------------------------------------------
@@ -68,21 +73,10 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t po
     return r;
 }
 __device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v));
 }
 __device__ __forceinline__ void red_or_b32(uint32_t* p, uint32_t v) {
-    asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Locate the path that owns global chunk index `c`: the last p with chunk_prefix[p] <= c.
-__device__ __forceinline__ uint32_t find_path(const uint32_t* __restrict__ prefix, uint32_t lo,
-                                              uint32_t hi, uint32_t c) {
-    // invariant: prefix[lo] <= c < prefix[hi]
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(prefix + mid) <= c) lo = mid; else hi = mid;
-    }
-    return lo;
+    asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v));
 }
 
 // 16-byte-vector index swizzle for the staged chunk: conflict-free for the coalesced
@@ -102,70 +96,95 @@ __device__ __forceinline__ uint32_t keep(uint32_t v) { asm volatile("mov.b32 %0,
 template <typename T>
 __device__ __forceinline__ T* keep_ptr(T* p) { asm volatile("mov.b64 %0, %0;" : "+l"(p)); return p; }
 
-__device__ __forceinline__ void load_thread_steps(uint32_t (&h)[kItems], const uint4* ld_base,
-                                                  uint32_t ld_lo, uint32_t swc) {
-#pragma unroll
-    for (int j = 0; j < kItems / 4; ++j) {
-        const uint4 x = ld_base[(ld_lo + j) ^ swc];
-        h[4 * j + 0] = x.x; h[4 * j + 1] = x.y; h[4 * j + 2] = x.z; h[4 * j + 3] = x.w;
-    }
+// ---------------------------------------------------------------------------
+// kernel A (k_step_stream_merged): one pass over the steps pool.
+//
+// Per chunk (kChunk consecutive steps of one path):
+//   stage   the chunk is copied global -> shared with 16-byte cp.async (L2 evict-first),
+//           double buffered: the copy of the block's NEXT chunk is in flight while the
+//           current one is processed, so HBM latency is off the critical path;
+//   pass 2  thread order: each thread walks its kItems consecutive steps, merges the
+//           seen-bitmap updates of steps that fall into the same 32-segment word in a
+//           register and issues ONE RED.OR per run (depth.rs:30-34 without the serial test);
+//   pass 3  lane order: lane l of each warp instruction handles consecutive step l, so
+//           the depth RED.ADDs (depth.rs:29) of a near-monotone walk coalesce into few
+//           L2 sector requests.
+// uniq comes from kernel B; depth is complete after this kernel.
+// Interior ("full") chunks take straight-line code; chunks that touch a path boundary
+// or the pool end are staged element-wise with an invalid-handle filler.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, uint64_t pol) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(pol)
+                 : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+constexpr uint32_t kFiller = 0xFFFFFFFFu;   // never a valid handle: segment ids are < 2^31
 
-// ---------------------------------------------------------------------------
-// kernel A, merged-direct form.
-// Same staging as the first-touch form, but no returning atomics: pass 2 merges the
-// seen-bitmap updates of each thread's consecutive steps into one RED.OR per run,
-// pass 3 issues one depth RED.ADD per step in lane order.  uniq comes from kernel B;
-// depth is complete after this kernel (kernel B must NOT add the first visits).
-// ---------------------------------------------------------------------------
 template <int BLOCKS_PER_SM, bool WITH_SEEN>
 __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(StreamParams P) {
-    __shared__ uint4 s_steps[kChunk / 4];
+    __shared__ uint4 s_steps[2][kChunk / 4];
     const uint64_t pol = make_evict_first_policy();
-    const uint32_t c_lo = __ldg(P.chunk_prefix + P.path_lo);
-    const uint32_t c_hi = __ldg(P.chunk_prefix + P.path_hi);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t seg_limit = P.n_segs * 2u;
-    uint4* const st_ptr = s_steps + swz(tid);
-    const uint32_t swc = (tid >> 1) & 7u;
-    const uint4* const ld_base = s_steps + ((tid * 4u) & ~7u);
-    const uint32_t ld_lo = 4u * (tid & 1u);
-    const uint32_t* const s_words = reinterpret_cast<const uint32_t*>(s_steps);
-    const uint32_t* const p3_ptr = keep_ptr(s_words + ((warp * 8u + ((lane >> 2) ^ (warp & 7u))) * 4u + (lane & 3u)));
+    const uint32_t seg_limit = P.n_segs * 2u;   // h < seg_limit  <=>  (h >> 1) < n_segs  (n_segs < 2^31)
+    const uint32_t st_off = swz(tid);                               // staging: vector tid + j*kThreads
+    const uint32_t swc = (tid >> 1) & 7u;                           // pass 2: vectors 4*tid + j
+    const uint32_t ld_base = (tid * 4u) & ~7u, ld_lo = 4u * (tid & 1u);
+    // pass 3: element i*kThreads + tid lives in vector i*64 + warp*8 + lane/4
+    const uint32_t p3_off = (warp * 8u + ((lane >> 2) ^ (warp & 7u))) * 4u + (lane & 3u);
     uint32_t* const depth_ptr = keep_ptr(P.depth);
-    const uint32_t one = keep(1u);
 
-    for (uint32_t c = c_lo + blockIdx.x; c < c_hi; c += gridDim.x) {
-        const uint32_t p = find_path(P.chunk_prefix, P.path_lo, P.path_hi, c);
-        const uint32_t s = __ldg(P.span_start + p), e = __ldg(P.span_end + p);
-        const uint64_t a = (uint64_t)(s & ~3u) + (uint64_t)(c - __ldg(P.chunk_prefix + p)) * kChunk;
-        uint32_t* __restrict__ row = P.bitmap + (size_t)(p - P.path_lo) * P.words_per_row;
-        const bool full = a >= s && a + kChunk <= e && a + kChunk <= P.n_steps;
-
-        // ---- pass 1: stage; out-of-span slots are filled with an invalid handle ----
+    auto stage = [&](uint4* buf, const ChunkDesc& d) {
+        const bool full = d.a >= d.s && (uint64_t)d.a + kChunk <= d.e;
         if (full) {
-            const uint32_t* src = P.steps + a + tid * 4u;
+            const uint32_t* src = P.steps + d.a + tid * 4u;
 #pragma unroll
-            for (int j = 0; j < kItems / 4; ++j)
-                st_ptr[j * kThreads] = ld_stream_v4(src + j * kThreads * 4, pol);
+            for (int j = 0; j < kItems / 4; ++j) cp_async_16(buf + st_off + j * kThreads, src + j * kThreads * 4, pol);
         } else {
 #pragma unroll
             for (int j = 0; j < kItems / 4; ++j) {
-                const uint64_t idx = a + (uint64_t)(tid + j * kThreads) * 4;
+                const uint64_t idx = (uint64_t)d.a + (uint64_t)(tid + j * kThreads) * 4;
                 uint32_t x[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    x[k] = (idx + k >= s && idx + k < e) ? P.steps[idx + k] : 0xFFFFFFFFu;
-                st_ptr[j * kThreads] = make_uint4(x[0], x[1], x[2], x[3]);
+                for (int k = 0; k < 4; ++k) x[k] = (idx + k >= d.s && idx + k < d.e) ? P.steps[idx + k] : kFiller;
+                buf[st_off + j * kThreads] = make_uint4(x[0], x[1], x[2], x[3]);
             }
         }
+    };
+
+    uint32_t c = P.chunk_lo + blockIdx.x;
+    if (c >= P.chunk_hi) return;
+    ChunkDesc cur = P.chunks[c];
+    stage(s_steps[0], cur);
+    cp_async_commit();
+    // descriptors are fetched two chunks ahead so their latency never gates a copy
+    ChunkDesc nxt = cur;
+    if (c + gridDim.x < P.chunk_hi) nxt = P.chunks[c + gridDim.x];
+    uint32_t b = 0;
+    for (; c < P.chunk_hi; c += gridDim.x) {
+        const uint32_t cn = c + gridDim.x;
+        ChunkDesc nxt2 = nxt;
+        if (cn < P.chunk_hi) {
+            if (cn + gridDim.x < P.chunk_hi) nxt2 = P.chunks[cn + gridDim.x];
+            stage(s_steps[b ^ 1], nxt);          // prefetch the next chunk while this one is processed
+        }
+        cp_async_commit();
+        cp_async_wait<1>();                      // this chunk's copies have landed
         __syncthreads();
 
+        const uint4* buf = s_steps[b];
         // ---- pass 2: thread order -- one RED.OR per run of steps in the same bitmap word ----
         if (WITH_SEEN) {
+            uint32_t* __restrict__ row = P.bitmap + (size_t)(cur.path - P.path_lo) * P.words_per_row;
             uint32_t h[kItems];
-            load_thread_steps(h, ld_base, ld_lo, swc);
+#pragma unroll
+            for (int j = 0; j < kItems / 4; ++j) {
+                const uint4 x = buf[ld_base + ((ld_lo + j) ^ swc)];
+                h[4 * j + 0] = x.x; h[4 * j + 1] = x.y; h[4 * j + 2] = x.z; h[4 * j + 3] = x.w;
+            }
             uint32_t hmax = 0;
 #pragma unroll
             for (int i = 0; i < kItems; ++i) hmax = max(hmax, h[i]);
@@ -179,32 +198,30 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
                         red_or_b32(row + (h[i] >> 6), acc);
                 }
             } else {
-                // edge chunk (invalid filler) or out-of-range segment id: per-step, unmerged
+                // filler (edge chunk) or out-of-range segment id somewhere: per step, unmerged
 #pragma unroll
                 for (int i = 0; i < kItems; ++i) {
                     if (h[i] < seg_limit) red_or_b32(row + (h[i] >> 6), bit_of(h[i] >> 1));
-                    else if (h[i] != 0xFFFFFFFFu) *P.err = 1u;
+                    else if (h[i] != kFiller) *P.err = 1u;
                 }
             }
         }
-
         // ---- pass 3: lane order -- one depth RED.ADD per step ----
-        if (full) {
+        {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(buf) + p3_off;
+            uint32_t hh[kItems];
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) hh[i] = w[i * kThreads];
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
-                const uint32_t hh = p3_ptr[i * kThreads];
-                if (hh < seg_limit) red_add_u32(depth_ptr + (hh >> 1), one);
-                else if (!WITH_SEEN) *P.err = 1u;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < kItems; ++i) {
-                const uint32_t hh = p3_ptr[i * kThreads];
-                if (hh < seg_limit) red_add_u32(depth_ptr + (hh >> 1), one);
-                else if (!WITH_SEEN && hh != 0xFFFFFFFFu) *P.err = 1u;
+                if (hh[i] < seg_limit) red_add_u32(depth_ptr + (hh[i] >> 1), 1u);
+                else if (!WITH_SEEN && hh[i] != kFiller) *P.err = 1u;
             }
         }
-        __syncthreads();
+        __syncthreads();                         // buffer b is free for the prefetch after next
+        cur = nxt;
+        nxt = nxt2;
+        b ^= 1;
     }
 }
 

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -13,26 +15,37 @@
 
 namespace {
 
-struct DeviceBuffers {
-    uint32_t* steps = nullptr;
-    uint32_t* depth = nullptr;
-    uint32_t* uniq = nullptr;
-    uint32_t* h_out = nullptr;   // pinned download staging
+// Process-wide workspace of the host-buffer entry points: device staging for the steps
+// pool and the outputs, pinned download staging, two streams, and the last plan.  It is
+// kept between calls (a 1.6 GB cudaMalloc + a pinned allocation + plan set-up would
+// otherwise cost more than the upload they serve) and released by
+// fgfa_release_workspace() or at process exit.  FGFA_WORKSPACE=0 disables the caching.
+struct Workspace {
+    std::mutex mu;
+    int device = -1;
+    uint32_t* steps = nullptr;  size_t steps_cap = 0;     // elements
+    uint32_t* out = nullptr;    size_t out_cap = 0;       // elements ([depth | uniq])
+    uint32_t* h_out = nullptr;  size_t h_out_cap = 0;     // pinned, elements
     cudaStream_t copy = nullptr, compute = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     fgfa_depth_plan_t* plan = nullptr;
-    ~DeviceBuffers() {
+    uint64_t plan_key[4] = {0, 0, 0, 0};
+
+    void release() {
         if (plan) fgfa_depth_plan_destroy(plan);
-        cudaFree(steps);
-        cudaFree(depth);
-        cudaFree(uniq);
+        plan = nullptr;
+        cudaFree(steps); steps = nullptr; steps_cap = 0;
+        cudaFree(out); out = nullptr; out_cap = 0;
         if (h_out) cudaFreeHost(h_out);
-        if (ev[0]) cudaEventDestroy(ev[0]);
-        if (ev[1]) cudaEventDestroy(ev[1]);
+        h_out = nullptr; h_out_cap = 0;
+        for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
         if (copy) cudaStreamDestroy(copy);
         if (compute) cudaStreamDestroy(compute);
+        copy = compute = nullptr;
+        device = -1;
     }
 };
+Workspace g_ws;
 
 int cuda_rc(cudaError_t e) {
     if (e == cudaSuccess) return FGFA_OK;
@@ -43,6 +56,44 @@ int cuda_rc(cudaError_t e) {
 #define CUH(x) do { int rc_ = cuda_rc(x); if (rc_) return rc_; } while (0)
 
 constexpr uint64_t kUploadGroupSteps = 16ull << 20;   // 64 MiB of Handle words per upload
+
+uint64_t fnv1a(const uint32_t* a, size_t n, uint64_t h) {
+    for (size_t i = 0; i < n; ++i) { h ^= a[i]; h *= 0x100000001B3ull; }
+    return h;
+}
+
+int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, bool want_uniq) {
+    int dev = 0;
+    CUH(cudaGetDevice(&dev));
+    if (w.device != dev) {
+        w.release();
+        CUH(cudaStreamCreateWithFlags(&w.copy, cudaStreamNonBlocking));
+        CUH(cudaStreamCreateWithFlags(&w.compute, cudaStreamNonBlocking));
+        CUH(cudaEventCreateWithFlags(&w.ev[0], cudaEventDisableTiming));
+        CUH(cudaEventCreateWithFlags(&w.ev[1], cudaEventDisableTiming));
+        w.device = dev;
+    }
+    const size_t need_steps = std::max<size_t>((size_t)n_steps, 4);
+    if (w.steps_cap < need_steps) {
+        cudaFree(w.steps); w.steps = nullptr; w.steps_cap = 0;
+        CUH(cudaMalloc(&w.steps, need_steps * 4));
+        w.steps_cap = need_steps;
+    }
+    const size_t need_out = std::max<size_t>((size_t)n_segs * 2, 2);
+    if (w.out_cap < need_out) {
+        cudaFree(w.out); w.out = nullptr; w.out_cap = 0;
+        CUH(cudaMalloc(&w.out, need_out * 4));
+        w.out_cap = need_out;
+    }
+    if (w.h_out_cap < need_out) {
+        if (w.h_out) cudaFreeHost(w.h_out);
+        w.h_out = nullptr; w.h_out_cap = 0;
+        CUH(cudaMallocHost(&w.h_out, need_out * 4));
+        w.h_out_cap = need_out;
+    }
+    (void)want_uniq;
+    return FGFA_OK;
+}
 
 void widen(const uint32_t* src, uint64_t* dst, size_t n) {
     const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
@@ -68,26 +119,34 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
                                    const uint32_t* h_span_start, const uint32_t* h_span_end,
                                    uint32_t n_paths, uint32_t n_segs, uint64_t* depth_out,
                                    uint64_t* uniq_out) {
-    if ((n_segs && !depth_out) || (n_steps && !h_steps)) return FGFA_ERR_INVALID_ARG;
+    if ((n_segs && !depth_out) || (n_steps && !h_steps) || (n_paths && (!h_span_start || !h_span_end)))
+        return FGFA_ERR_INVALID_ARG;
     if (fgfa_device_count() <= 0) return FGFA_ERR_NO_DEVICE;
-    DeviceBuffers B;
-    int rc = fgfa_depth_plan_create(&B.plan, h_span_start, h_span_end, n_paths, n_segs, n_steps, 0);
-    if (rc) return rc;
+    Workspace& W = g_ws;
+    std::lock_guard<std::mutex> lock(W.mu);
+    const char* env = std::getenv("FGFA_WORKSPACE");
+    const bool keep = !(env && env[0] == '0');
+    struct Releaser { Workspace& w; bool on; ~Releaser() { if (on) w.release(); } } releaser{W, !keep};
+
     const bool want_uniq = uniq_out != nullptr;
-    CUH(cudaStreamCreateWithFlags(&B.copy, cudaStreamNonBlocking));
-    CUH(cudaStreamCreateWithFlags(&B.compute, cudaStreamNonBlocking));
-    CUH(cudaEventCreateWithFlags(&B.ev[0], cudaEventDisableTiming));
-    CUH(cudaEventCreateWithFlags(&B.ev[1], cudaEventDisableTiming));
-    CUH(cudaMalloc(&B.steps, std::max<size_t>((size_t)n_steps * 4, 16)));
-    CUH(cudaMalloc(&B.depth, std::max<size_t>((size_t)n_segs * 4, 4)));
-    if (want_uniq) CUH(cudaMalloc(&B.uniq, std::max<size_t>((size_t)n_segs * 4, 4)));
-    CUH(cudaMallocHost(&B.h_out, std::max<size_t>((size_t)n_segs * 4 * (want_uniq ? 2 : 1), 4)));
-
-    rc = fgfa_depth_plan_begin(B.plan, B.depth, B.compute);
+    int rc = ensure_workspace(W, n_steps, n_segs, want_uniq);
     if (rc) return rc;
+    const uint64_t key[4] = {n_paths, n_segs, n_steps,
+                             fnv1a(h_span_end, n_paths, fnv1a(h_span_start, n_paths, 0xCBF29CE484222325ull))};
+    if (!W.plan || std::memcmp(key, W.plan_key, sizeof key) != 0) {
+        if (W.plan) fgfa_depth_plan_destroy(W.plan);
+        W.plan = nullptr;
+        rc = fgfa_depth_plan_create(&W.plan, h_span_start, h_span_end, n_paths, n_segs, n_steps, 0);
+        if (rc) return rc;
+        std::memcpy(W.plan_key, key, sizeof key);
+    }
+    uint32_t* d_depth = W.out;
+    uint32_t* d_uniq = want_uniq ? W.out + n_segs : nullptr;
 
+    rc = fgfa_depth_plan_begin(W.plan, d_depth, W.compute);
+    if (rc) return rc;
     // Are the spans laid out like the parser leaves them (pool order, disjoint)?  Then
-    // uploads and kernels can be pipelined group by group; otherwise upload everything first.
+    // uploads and kernels are pipelined group by group; otherwise upload everything first.
     bool monotone = true;
     for (uint32_t p = 1; p < n_paths && monotone; ++p) monotone = h_span_start[p] >= h_span_end[p - 1];
     if (monotone && n_paths) {
@@ -102,32 +161,34 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
             }
             const uint64_t a = h_span_start[lo], b = h_span_end[hi - 1];
             if (b > a)
-                CUH(cudaMemcpyAsync(B.steps + a, h_steps + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, B.copy));
-            CUH(cudaEventRecord(B.ev[slot], B.copy));
-            CUH(cudaStreamWaitEvent(B.compute, B.ev[slot], 0));
-            rc = fgfa_depth_plan_feed(B.plan, B.steps, lo, hi, B.depth, B.uniq, B.compute);
+                CUH(cudaMemcpyAsync(W.steps + a, h_steps + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, W.copy));
+            CUH(cudaEventRecord(W.ev[slot], W.copy));
+            CUH(cudaStreamWaitEvent(W.compute, W.ev[slot], 0));
+            rc = fgfa_depth_plan_feed(W.plan, W.steps, lo, hi, d_depth, d_uniq, W.compute);
             if (rc) return rc;
             slot ^= 1;
             lo = hi;
         }
     } else {
-        if (n_steps) CUH(cudaMemcpyAsync(B.steps, h_steps, (size_t)n_steps * 4, cudaMemcpyHostToDevice, B.compute));
-        rc = fgfa_depth_plan_feed(B.plan, B.steps, 0, n_paths, B.depth, B.uniq, B.compute);
+        if (n_steps) CUH(cudaMemcpyAsync(W.steps, h_steps, (size_t)n_steps * 4, cudaMemcpyHostToDevice, W.compute));
+        rc = fgfa_depth_plan_feed(W.plan, W.steps, 0, n_paths, d_depth, d_uniq, W.compute);
         if (rc) return rc;
     }
-    rc = fgfa_depth_plan_finish(B.plan, B.uniq, B.compute);
+    rc = fgfa_depth_plan_finish(W.plan, d_uniq, W.compute);
     if (rc) return rc;
-    if (n_segs) {
-        CUH(cudaMemcpyAsync(B.h_out, B.depth, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, B.compute));
-        if (want_uniq)
-            CUH(cudaMemcpyAsync(B.h_out + n_segs, B.uniq, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, B.compute));
-    }
-    rc = fgfa_depth_plan_status(B.plan, B.compute);   // synchronises
+    if (n_segs)
+        CUH(cudaMemcpyAsync(W.h_out, W.out, (size_t)n_segs * 4 * (want_uniq ? 2 : 1), cudaMemcpyDeviceToHost, W.compute));
+    rc = fgfa_depth_plan_status(W.plan, W.compute);   // synchronises the compute stream
     if (rc) return rc;
-    CUH(cudaStreamSynchronize(B.copy));
-    widen(B.h_out, depth_out, n_segs);
-    if (want_uniq) widen(B.h_out + n_segs, uniq_out, n_segs);
+    CUH(cudaStreamSynchronize(W.copy));
+    widen(W.h_out, depth_out, n_segs);
+    if (want_uniq) widen(W.h_out + n_segs, uniq_out, n_segs);
     return FGFA_OK;
+}
+
+void fgfa_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    g_ws.release();
 }
 
 int fgfa_flatgfa_counts(const void* bytes, size_t len, uint64_t* n_segs, uint64_t* n_paths,

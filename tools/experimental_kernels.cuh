@@ -5,6 +5,37 @@
 
 namespace fgfa {
 
+// The experimental kernels keep the earlier work decomposition (chunk prefix + binary search).
+struct ExpParams {
+    const uint32_t* __restrict__ steps;
+    uint64_t n_steps;
+    const uint32_t* __restrict__ span_start;
+    const uint32_t* __restrict__ span_end;
+    const uint32_t* __restrict__ chunk_prefix;
+    uint32_t path_lo, path_hi;
+    uint32_t n_segs;
+    uint32_t words_per_row;
+    uint32_t* __restrict__ depth;
+    uint32_t* __restrict__ bitmap;
+    uint32_t* __restrict__ err;
+};
+__device__ __forceinline__ uint32_t find_path(const uint32_t* __restrict__ prefix, uint32_t lo,
+                                              uint32_t hi, uint32_t c) {
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= c) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ void load_thread_steps(uint32_t (&h)[kItems], const uint4* ld_base,
+                                                  uint32_t ld_lo, uint32_t swc) {
+#pragma unroll
+    for (int j = 0; j < kItems / 4; ++j) {
+        const uint4 x = ld_base[(ld_lo + j) ^ swc];
+        h[4 * j + 0] = x.x; h[4 * j + 1] = x.y; h[4 * j + 2] = x.z; h[4 * j + 3] = x.w;
+    }
+}
+
 enum StreamMode : int {
     kModeDepthAndSeen = 0,   // the product configuration
     kModeDepthOnly = 1,      // seg_depth (depth.rs:45-56) and the roofline split
@@ -21,7 +52,7 @@ enum StreamMode : int {
 // LANE_ORDER=0: each thread handles 4 consecutive steps from one 128-bit load.
 // ---------------------------------------------------------------------------
 template <int MODE, int LANE_ORDER>
-__global__ void __launch_bounds__(kThreads) k_step_stream_direct(StreamParams P) {
+__global__ void __launch_bounds__(kThreads) k_step_stream_direct(ExpParams P) {
     const uint64_t pol = make_evict_first_policy();
     const uint32_t c_lo = __ldg(P.chunk_prefix + P.path_lo);
     const uint32_t c_hi = __ldg(P.chunk_prefix + P.path_hi);
@@ -156,7 +187,7 @@ __device__ __noinline__ uint32_t dup_mask(const uint4* ld_base, uint32_t ld_lo, 
 }
 
 template <int BLOCKS_PER_SM, int EXPERIMENT = 0>
-__global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_first_touch(StreamParams P) {
+__global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_first_touch(ExpParams P) {
     __shared__ uint4 s_steps[kChunk / 4];
     __shared__ uint32_t s_flags[kChunk / 32];   // bit l of word m: step 32m+l is a repeat visit
     const uint64_t pol = make_evict_first_policy();
@@ -271,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_first_t
 // repeat visits issue their depth RED in lane order straight away.
 // ---------------------------------------------------------------------------
 template <int BLOCKS_PER_SM>
-__global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_warp_agg(StreamParams P) {
+__global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_warp_agg(ExpParams P) {
     const uint64_t pol = make_evict_first_policy();
     const uint32_t c_lo = __ldg(P.chunk_prefix + P.path_lo);
     const uint32_t c_hi = __ldg(P.chunk_prefix + P.path_hi);

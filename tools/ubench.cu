@@ -87,10 +87,21 @@ int main(int argc, char** argv) {
     CK(cudaMemset(d_bitmap, 0, (size_t)cfg.n_paths * wpr * 4));
     CK(cudaMemset(d_err, 0, 4));
 
-    StreamParams P{};
+    ExpParams P{};
     P.steps = d_steps; P.n_steps = cfg.n_steps; P.span_start = d_ss; P.span_end = d_se;
     P.chunk_prefix = d_prefix; P.path_lo = 0; P.path_hi = cfg.n_paths; P.n_segs = cfg.n_segs;
     P.words_per_row = wpr; P.depth = d_depth; P.bitmap = d_bitmap; P.err = d_err;
+    std::vector<ChunkDesc> table(n_chunks);
+    for (uint32_t p = 0; p < cfg.n_paths; ++p) {
+        uint64_t a = ss[p] & ~3u;
+        for (uint32_t c = prefix[p]; c < prefix[p + 1]; ++c, a += kChunk) table[c] = ChunkDesc{(uint32_t)a, ss[p], se[p], p};
+    }
+    ChunkDesc* d_chunks;
+    CK(cudaMalloc(&d_chunks, std::max<size_t>(n_chunks, 1) * sizeof(ChunkDesc)));
+    CK(cudaMemcpy(d_chunks, table.data(), (size_t)n_chunks * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
+    StreamParams S{};
+    S.steps = d_steps; S.chunks = d_chunks; S.chunk_lo = 0; S.chunk_hi = n_chunks; S.path_lo = 0;
+    S.n_segs = cfg.n_segs; S.words_per_row = wpr; S.depth = d_depth; S.bitmap = d_bitmap; S.err = d_err;
     PopcountParams Q{};
     Q.bitmap = d_bitmap; Q.n_rows = cfg.n_paths; Q.words_per_row = wpr; Q.n_words = n_words;
     Q.n_segs = cfg.n_segs; Q.uniq = d_uniq; Q.depth = nullptr; Q.accumulate = 0;
@@ -199,10 +210,12 @@ int main(int argc, char** argv) {
         }
         time_it("depth-only half-lanes(seg even) g=8xSM", [&] { k_step_stream_direct<kModeDepthHalfLanes, 1><<<sms * 8, kThreads>>>(P); }, false);
         time_it("depth-only pairs(+2 even tid) g=8xSM", [&] { k_step_stream_direct<kModeDepthPairs, 1><<<sms * 8, kThreads>>>(P); }, false);
-        time_it("merged depth+seen g=4xSM", [&] { k_step_stream_merged<4, true><<<sms * 4, kThreads>>>(P); }, true);
-        time_it("merged depth+seen g=6xSM", [&] { k_step_stream_merged<6, true><<<sms * 6, kThreads>>>(P); }, true);
-        time_it("merged depth+seen g=8xSM", [&] { k_step_stream_merged<8, true><<<sms * 8, kThreads>>>(P); }, true);
-        time_it("merged depth-only g=8xSM", [&] { k_step_stream_merged<8, false><<<sms * 8, kThreads>>>(P); }, true);
+        time_it("merged depth+seen g=4xSM", [&] { k_step_stream_merged<4, true><<<sms * 4, kThreads>>>(S); }, true);
+        time_it("merged depth+seen g=6xSM", [&] { k_step_stream_merged<6, true><<<sms * 6, kThreads>>>(S); }, true);
+        time_it("merged depth+seen g=5xSM", [&] { k_step_stream_merged<5, true><<<sms * 5, kThreads>>>(S); }, true);
+        time_it("merged depth+seen g=6x2", [&] { k_step_stream_merged<6, true><<<sms * 12, kThreads>>>(S); }, true);
+        time_it("merged depth+seen g=8xSM", [&] { k_step_stream_merged<8, true><<<sms * 8, kThreads>>>(S); }, true);
+        time_it("merged depth-only g=8xSM", [&] { k_step_stream_merged<8, false><<<sms * 8, kThreads>>>(S); }, true);
         time_it("warp-agg A only g=4xSM", [&] { k_step_stream_warp_agg<4><<<sms * 4, kThreads>>>(P); }, true);
         time_it("warp-agg A only g=6xSM", [&] { k_step_stream_warp_agg<6><<<sms * 6, kThreads>>>(P); }, true);
         time_it("warp-agg A only g=8xSM", [&] { k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); }, true);
@@ -217,7 +230,7 @@ int main(int argc, char** argv) {
             for (int r = 0; r < reps + 2; ++r) {
                 CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
-                if (use_merged) k_step_stream_merged<8, true><<<sms * 8, kThreads>>>(P); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
+                if (use_merged) k_step_stream_merged<8, true><<<sms * 8, kThreads>>>(S); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
                 k_uniq_popcount<<<pgrid, kPopThreads>>>(Q2);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
