@@ -218,3 +218,22 @@ def test_synth_is_deterministic_and_shaped():
     assert rc == 0 and int(d.sum()) == cfg.n_steps
     assert int(d.max()) > 50            # the hot windows really are hot
     assert (u <= np.minimum(d, cfg.n_paths)).all()
+
+
+def test_reference_c_example_builds_and_runs_unchanged(tmp_path):
+    """flatgfa-c/example/example.c (includes "../include/flatgfa.h") against this library.
+    Needs the reference checkout, which only the build container has."""
+    src = "/root/reference/flatgfa-c/example/example.c"
+    if not os.path.exists(src):
+        pytest.skip("reference checkout not present")
+    (tmp_path / "include").mkdir()
+    (tmp_path / "example").mkdir()
+    import shutil
+    shutil.copy(os.path.join(ROOT, "include", "flatgfa.h"), tmp_path / "include" / "flatgfa.h")
+    shutil.copy(src, tmp_path / "example" / "example.c")
+    libdir = os.path.join(ROOT, "pollen_b200", "lib")
+    subprocess.run(["gcc", "-w", "example.c", "-L" + libdir, "-lflatgfa", "-Wl,-rpath," + libdir, "-o", "example"],
+                   cwd=tmp_path / "example", check=True)
+    out = subprocess.run(["./example", os.path.join(GOLD, "ref_tiny.gfa")], cwd=tmp_path / "example",
+                         capture_output=True, check=True).stdout
+    assert out == b"one:\n  + CAAATAAG\n  + AAATTTTCTGGAGTTCTAT\ntwo:\n  + CAAATAAG\n  + AAATTTTCTGGAGTTCTAT\n"
