@@ -183,7 +183,7 @@ def main():
     h_steps = torch.from_numpy(h_steps_np.view(np.int32)).pin_memory()      # pinned host copy for e2e
     d_steps = torch.empty(n_local, dtype=torch.int32, device=dev)
     d_steps.copy_(h_steps)
-    eng = sharding.ShardedDepth(ls, le, cfg.n_segs, dev)
+    eng = sharding.ShardedDepth(ls, le, cfg.n_segs, dev, n_paths_global=cfg.n_paths if world > 1 else None)
     stream = torch.cuda.current_stream(dev)
     launches_per_step = eng.plan.launches(True)
 
@@ -235,6 +235,38 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "whole_step_frac": (4.0 * cfg.n_steps + 8.0 * cfg.n_paths + 8.0 * cfg.n_segs) / world / (ms_per_step * 1e-3) / 1e9 / peak}
 
+    roofline["frac_of_nominal_8tbs"] = achieved / 8000.0
+    try:   # DRAM traffic of one kernel-A launch from the committed `ncu --set full` capture (N=1, config C)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(f"{cfg.name}:{world}")
+        if t:
+            roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+            roofline["traffic_source"] = t["source"]
+    except Exception:
+        pass
+
+    # ---- split: depth only (seg_depth, depth.rs:45-56) and the collective alone ---------
+    def timed(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        barrier()
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    depth_only_ms = timed(lambda: eng.plan.run(d_steps, eng.depth, None, stream.cuda_stream), args.steps)
+    allreduce_ms = timed(lambda: sharding.allreduce_counts(eng.out), args.steps) if world > 1 else 0.0
+    eng.run(d_steps, stream)          # leave a valid result behind
+    eng.status()
+    split = {"depth_only_ms_per_step": depth_only_ms, "depth_only_steps_per_s": cfg.n_steps / (depth_only_ms * 1e-3),
+             "allreduce_ms": allreduce_ms, "allreduce_bytes": eng.exchange_bytes if world > 1 else 0,
+             "stream_kernel_ms": k_ms}
+
     # ---- end to end: host buffers in, host results out ---------------------------------
     e2e_steps = max(1, args.e2e_steps)
     if world == 1:
@@ -258,12 +290,13 @@ def main():
         assert int(d64.sum()) == cfg.n_steps
         e2e_api = "fgfa_seg_depth_with_uniq_steps (C ABI, pinned host steps)"
     else:
-        out_host = torch.empty(2 * cfg.n_segs, dtype=torch.int32).pin_memory()
+        out_host = torch.empty(eng.out.numel(), dtype=torch.int32).pin_memory()
 
         def e2e_once():
             d_steps.copy_(h_steps, non_blocking=True)
             eng.run(d_steps, stream)
-            out_host.copy_(eng.out, non_blocking=True)
+            if rank == 0:                      # the table is printed by one process
+                out_host.copy_(eng.out, non_blocking=True)
             stream.synchronize()
         e2e_once()
         barrier()
@@ -276,7 +309,7 @@ def main():
         e2e_s = float(e2e_t.item())
         e2e_api = "ShardedDepth.run on pinned host shards (H2D + kernels + NCCL allreduce + D2H)"
     e2e = {"value": cfg.n_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local + 8 * len(my_paths),
-           "d2h_bytes_per_step": 8 * cfg.n_segs, "ms_per_step": e2e_s * 1e3, "api": e2e_api, "steps": e2e_steps}
+           "d2h_bytes_per_step": eng.exchange_bytes if world > 1 else 8 * cfg.n_segs, "ms_per_step": e2e_s * 1e3, "api": e2e_api, "steps": e2e_steps}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------
     cpu = None
@@ -291,7 +324,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload_config(cfg, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "config": workload_config(cfg, world), "roofline": roofline, "split": split, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }))
     if world > 1:

@@ -87,6 +87,12 @@ int fgfa_depth_plan_finish(fgfa_depth_plan_t* plan, uint32_t* d_uniq, void* cuda
  * last call: FGFA_OK, FGFA_ERR_SEG_OOB or FGFA_ERR_CUDA. */
 int fgfa_depth_plan_status(fgfa_depth_plan_t* plan, void* cuda_stream);
 
+/* Width of the uniq counters the plan's runs write to d_uniq: 4 (default, u32) or 1 (u8;
+ * only for plans of <= 255 paths, since uniq <= n_paths).  The narrow form exists for the
+ * multi-GPU exchange: [depth u32 | uniq u8] is 25 MB instead of 40 MB at 5 M segments, and
+ * packed bytes can be summed as u32 words because no global uniq exceeds 255 either. */
+int fgfa_depth_plan_set_uniq_width(fgfa_depth_plan_t* plan, int bytes);
+
 /* Measurement hook: the next fgfa_depth_plan_run/feed records `before` immediately
  * before and `after` immediately after its step-stream kernel launches (CUDA events
  * owned by the caller, timing enabled).  Pass NULLs to clear.  One-shot: cleared after

@@ -73,6 +73,7 @@ EXPORTS = {
     "fgfa_depth_plan_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_set_uniq_width": (C.c_int, [C.c_void_p, C.c_int]),
     "fgfa_depth_plan_set_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_launches": (C.c_uint32, [C.c_void_p, C.c_int]),
     "fgfa_depth_plan_scratch_bytes": (C.c_size_t, [C.c_void_p]),
@@ -290,6 +291,10 @@ class DepthPlan:
     def status(self, stream: int = 0) -> None:
         """Synchronise and raise DepthError if a run saw an out-of-range segment id."""
         _check(lib().fgfa_depth_plan_status(self._h, stream or None))
+
+    def set_uniq_width(self, nbytes: int) -> None:
+        """uniq counters as u32 (4, default) or u8 (1; plans of <= 255 paths)."""
+        _check(lib().fgfa_depth_plan_set_uniq_width(self._h, nbytes))
 
     def set_probe(self, before_event: int, after_event: int) -> None:
         """Record the given CUDA events around the next run's step-stream kernel."""

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -59,6 +60,8 @@ struct fgfa_depth_plan {
     uint32_t* d_bitmap = nullptr;          // [rows_per_batch][words_per_row], zero between runs
     uint32_t* d_err = nullptr;
     size_t scratch_bytes = 0;
+    int uniq_bytes = 4;                    // width of the uniq counters kernel B writes
+    int seen_mode = fgfa::kSeenDirect;     // how kernel A records seen-bits (see depth_kernels.cuh)
     cudaEvent_t probe_before = nullptr, probe_after = nullptr;   // one-shot measurement hook
     uint32_t next_path = 0;                // begin/feed/finish cursor
     bool uniq_started = false;
@@ -114,10 +117,15 @@ int launch_stream(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     P.err = pl->d_err;
     const uint32_t grid = std::min<uint32_t>(chunks, (uint32_t)pl->sms * kBlocksPerSM);
     if (pl->probe_before) CU(cudaEventRecord(pl->probe_before, st));
-    if (with_seen)
-        fgfa::k_step_stream_merged<kBlocksPerSM, true><<<grid, fgfa::kThreads, 0, st>>>(P);
+    if (with_seen && pl->seen_mode == fgfa::kSeenWindow)
+        fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenWindow>
+            <<<grid, fgfa::kThreads, fgfa::stream_smem_bytes(fgfa::kSeenWindow), st>>>(P);
+    else if (with_seen)
+        fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenDirect>
+            <<<grid, fgfa::kThreads, fgfa::stream_smem_bytes(fgfa::kSeenDirect), st>>>(P);
     else
-        fgfa::k_step_stream_merged<kBlocksPerSM, false><<<grid, fgfa::kThreads, 0, st>>>(P);
+        fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenNone>
+            <<<grid, fgfa::kThreads, fgfa::stream_smem_bytes(fgfa::kSeenNone), st>>>(P);
     CU(cudaGetLastError());
     if (pl->probe_after) CU(cudaEventRecord(pl->probe_after, st));
     pl->probe_before = pl->probe_after = nullptr;
@@ -136,6 +144,7 @@ int launch_popcount(fgfa_depth_plan* pl, uint32_t rows, uint32_t* d_uniq, bool a
     Q.uniq = d_uniq;
     Q.depth = nullptr;
     Q.accumulate = accumulate ? 1 : 0;
+    Q.uniq_bytes = pl->uniq_bytes;
     const uint32_t grid = (pl->n_words + fgfa::kPopThreads - 1) / fgfa::kPopThreads;
     fgfa::k_uniq_popcount<<<grid, fgfa::kPopThreads, 0, st>>>(Q);
     CU(cudaGetLastError());
@@ -212,7 +221,10 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
     pl->n_words = (n_segs + 31) / 32;
     pl->words_per_row = (pl->n_words + 31) & ~31u;  // 128-byte row pitch
     const size_t row_bytes = (size_t)pl->words_per_row * 4;
-    const size_t budget = bitmap_budget_bytes ? bitmap_budget_bytes : kDefaultBitmapBudget;
+    size_t budget = bitmap_budget_bytes ? bitmap_budget_bytes : kDefaultBitmapBudget;
+    if (!bitmap_budget_bytes)
+        if (const char* env = std::getenv("FGFA_BITMAP_BUDGET_MB"))
+            if (std::atoll(env) > 0) budget = (size_t)std::atoll(env) << 20;
     uint64_t rows = row_bytes ? std::max<uint64_t>(1, budget / row_bytes) : 1;
     rows = std::min<uint64_t>(rows, std::max<uint32_t>(1u, n_paths));
     pl->rows_per_batch = (uint32_t)rows;
@@ -224,8 +236,23 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
     CUB_(cudaMemset(pl->d_err, 0, 4));
 #undef CUB_
     // kernel A wants 6 CTAs x 32 KiB of shared memory per SM: ask for the large carve-out
-    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenWindow>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::stream_smem_bytes(fgfa::kSeenWindow));
+    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenDirect>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenNone>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    // Seen-bit strategy.  Paths that are much longer than the graph has segments must loop
+    // (config E: tandem repeats), so their chunks keep hitting the same bitmap sectors and
+    // the shared-memory window pays off (measured 1.30 -> 1.09 ms on E); for haplotype-like
+    // paths the direct form is faster (0.73 vs 0.95 ms on C).  FGFA_SEEN_MODE overrides.
+    {
+        uint64_t longest = 0;
+        for (uint32_t p = 0; p < n_paths; ++p) longest = std::max<uint64_t>(longest, (uint64_t)h_span_end[p] - h_span_start[p]);
+        pl->seen_mode = (longest > 4ull * std::max<uint32_t>(n_segs, 1u)) ? fgfa::kSeenWindow : fgfa::kSeenDirect;
+        if (const char* env = std::getenv("FGFA_SEEN_MODE")) {
+            if (!std::strcmp(env, "window")) pl->seen_mode = fgfa::kSeenWindow;
+            else if (!std::strcmp(env, "direct")) pl->seen_mode = fgfa::kSeenDirect;
+        }
+    }
     int rc = build_tables(pl, 0);
     if (rc) return bail(rc);
     pl->scratch_bytes = bitmap_bytes + pl->chunk_capacity * sizeof(fgfa::ChunkDesc) + 4;
@@ -285,7 +312,7 @@ int fgfa_depth_plan_finish(fgfa_depth_plan_t* pl, uint32_t* d_uniq, void* cuda_s
     if (!pl) return fail(FGFA_ERR_INVALID_ARG, "null plan");
     if (pl->next_path != pl->n_paths) return fail(FGFA_ERR_INVALID_ARG, "not all paths were fed");
     if (d_uniq && !pl->uniq_started && pl->n_segs)  // no paths at all: uniq is all zero
-        CU(cudaMemsetAsync(d_uniq, 0, (size_t)pl->n_segs * 4, (cudaStream_t)cuda_stream));
+        CU(cudaMemsetAsync(d_uniq, 0, (size_t)pl->n_segs * pl->uniq_bytes, (cudaStream_t)cuda_stream));
     return FGFA_OK;
 }
 
@@ -309,6 +336,13 @@ int fgfa_depth_plan_status(fgfa_depth_plan_t* pl, void* cuda_stream) {
         CU(cudaStreamSynchronize(st));
         return fail(FGFA_ERR_SEG_OOB, "a step refers to a segment index >= n_segs");
     }
+    return FGFA_OK;
+}
+
+int fgfa_depth_plan_set_uniq_width(fgfa_depth_plan_t* pl, int bytes) {
+    if (!pl || (bytes != 1 && bytes != 4)) return fail(FGFA_ERR_INVALID_ARG, "uniq width must be 1 or 4 bytes");
+    if (bytes == 1 && pl->n_paths > 255) return fail(FGFA_ERR_INVALID_ARG, "u8 uniq counters need <= 255 paths");
+    pl->uniq_bytes = bytes;
     return FGFA_OK;
 }
 

@@ -124,9 +124,44 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr uint32_t kFiller = 0xFFFFFFFFu;   // never a valid handle: segment ids are < 2^31
 
-template <int BLOCKS_PER_SM, bool WITH_SEEN>
+// How kernel A records the seen-bits:
+//   kSeenNone    seg_depth only (depth.rs:45-56), no bitmap;
+//   kSeenDirect  one RED.OR per thread-level run, straight to L2;
+//   kSeenWindow  thread-level runs are first OR-ed into a block-wide shared-memory window
+//                (direct-mapped by bitmap-word index, one tag per 32-byte bitmap sector),
+//                then every touched sector is flushed with ONE coalesced RED.OR request.
+//                A chunk re-visits the same bitmap sectors many times (a sector covers 256
+//                segments), so this cuts the L2 reduction sectors of the seen-bits ~3-4x.
+enum SeenMode : int { kSeenNone = 0, kSeenDirect = 1, kSeenWindow = 2 };
+
+constexpr uint32_t kWinWords = 4096;              // window: 4096 bitmap words = 131072 segments
+constexpr uint32_t kWinGroups = kWinWords / 8;    // one tag per bitmap sector (8 words)
+constexpr uint32_t kTagEmpty = 0xFFFFFFFFu;
+
+__host__ __device__ constexpr size_t stream_smem_bytes(int seen_mode) {
+    return 2 * (size_t)kChunk * 4 +
+           (seen_mode == kSeenWindow ? (size_t)kWinWords * 4 + kWinGroups * 4 + kWinGroups * 4 + 16 : 0);
+}
+
+__device__ __forceinline__ void red_shared_or(uint32_t* p, uint32_t v) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+template <int BLOCKS_PER_SM, int SEEN_MODE>
 __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(StreamParams P) {
-    __shared__ uint4 s_steps[2][kChunk / 4];
+    constexpr bool WITH_SEEN = SEEN_MODE != kSeenNone;
+    extern __shared__ uint4 smem_dyn[];
+    uint4 (*s_steps)[kChunk / 4] = reinterpret_cast<uint4 (*)[kChunk / 4]>(smem_dyn);
+    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(smem_dyn + 2 * (kChunk / 4));   // [kWinWords]
+    uint32_t* const s_tag = s_bits + kWinWords;                                          // [kWinGroups]
+    uint32_t* const s_list = s_tag + kWinGroups;                                         // [kWinGroups]
+    uint32_t* const s_count = s_list + kWinGroups;
+    if (SEEN_MODE == kSeenWindow) {
+        for (uint32_t i = threadIdx.x; i < kWinWords; i += kThreads) s_bits[i] = 0u;
+        for (uint32_t i = threadIdx.x; i < kWinGroups; i += kThreads) s_tag[i] = kTagEmpty;
+        if (threadIdx.x == 0) *s_count = 0u;
+    }
     const uint64_t pol = make_evict_first_policy();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t seg_limit = P.n_segs * 2u;   // h < seg_limit  <=>  (h >> 1) < n_segs  (n_segs < 2^31)
@@ -194,8 +229,24 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
                 for (int i = 0; i < kItems; ++i) {
                     const uint32_t bit = bit_of(h[i] >> 1);
                     acc = ((i > 0 && ((h[i] ^ h[i - 1]) < 64u)) ? acc : 0u) | bit;
-                    if (i == kItems - 1 || ((h[i] ^ h[i + (i < kItems - 1)]) >= 64u))
-                        red_or_b32(row + (h[i] >> 6), acc);
+                    if (i == kItems - 1 || ((h[i] ^ h[i + (i < kItems - 1)]) >= 64u)) {
+                        const uint32_t w = h[i] >> 6;
+                        if (SEEN_MODE == kSeenWindow) {
+                            const uint32_t g = (w >> 3) & (kWinGroups - 1), tag = w >> 12;
+                            uint32_t t = s_tag[g];
+                            if (t == kTagEmpty) {
+                                t = atomicCAS(&s_tag[g], kTagEmpty, tag);
+                                if (t == kTagEmpty) {            // this thread claimed the sector
+                                    t = tag;
+                                    s_list[atomicAdd(s_count, 1u)] = g;
+                                }
+                            }
+                            if (t == tag) red_shared_or(&s_bits[w & (kWinWords - 1)], acc);
+                            else red_or_b32(row + w, acc);       // window slot taken by another sector
+                        } else {
+                            red_or_b32(row + w, acc);
+                        }
+                    }
                 }
             } else {
                 // filler (edge chunk) or out-of-range segment id somewhere: per step, unmerged
@@ -218,7 +269,28 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
                 else if (!WITH_SEEN && hh[i] != kFiller) *P.err = 1u;
             }
         }
-        __syncthreads();                         // buffer b is free for the prefetch after next
+        if (SEEN_MODE == kSeenWindow) {
+            // ---- flush: one coalesced RED.OR request per touched bitmap sector ----
+            uint32_t* __restrict__ row = P.bitmap + (size_t)(cur.path - P.path_lo) * P.words_per_row;
+            __syncthreads();
+            const uint32_t n = *s_count * 8u;            // 8 lanes per touched sector, block-uniform
+            for (uint32_t base = warp * 32u; base < n; base += kThreads) {   // warp-uniform trip count
+                const uint32_t i = base + lane;
+                const bool on = i < n;
+                const uint32_t g = on ? s_list[i >> 3] : 0u, slot = (g << 3) | (i & 7u);
+                const uint32_t v = on ? s_bits[slot] : 0u, tag = s_tag[g];
+                if (v) {
+                    red_or_b32(row + ((tag << 12) | slot), v);
+                    s_bits[slot] = 0u;
+                }
+                __syncwarp();                            // every lane has read the tag
+                if (on && (i & 7u) == 0u) s_tag[g] = kTagEmpty;
+            }
+            __syncthreads();
+            if (tid == 0) *s_count = 0u;
+        } else {
+            __syncthreads();                     // buffer b is free for the prefetch after next
+        }
         cur = nxt;
         nxt = nxt2;
         b ^= 1;
@@ -242,9 +314,10 @@ struct PopcountParams {
     uint32_t words_per_row;
     uint32_t n_words;                // ceil(n_segs / 32)
     uint32_t n_segs;
-    uint32_t* __restrict__ uniq;     // [n_segs] or nullptr (seg_depth: no unique depth)
+    void* __restrict__ uniq;         // [n_segs] u32 (or u8, see uniq_bytes) or nullptr
     uint32_t* __restrict__ depth;    // [n_segs] or nullptr
     int accumulate;                  // 0: uniq = cnt, 1: uniq += cnt
+    int uniq_bytes;                  // 4: u32 counters; 1: u8 counters (caller guarantees <= 255 paths)
 };
 
 constexpr int kPopThreads = 128;
@@ -300,7 +373,15 @@ __global__ void __launch_bounds__(kPopThreads) k_uniq_popcount(PopcountParams P)
         const uint64_t seg = ((uint64_t)(w_base + k) << 5) + lane;
         if (seg < P.n_segs) {
             const uint32_t v = tile[warp][k][lane];
-            if (P.uniq) { if (P.accumulate) P.uniq[seg] += v; else P.uniq[seg] = v; }
+            if (P.uniq) {
+                if (P.uniq_bytes == 1) {
+                    uint8_t* u = static_cast<uint8_t*>(P.uniq);
+                    u[seg] = (uint8_t)(P.accumulate ? u[seg] + v : v);
+                } else {
+                    uint32_t* u = static_cast<uint32_t*>(P.uniq);
+                    if (P.accumulate) u[seg] += v; else u[seg] = v;
+                }
+            }
             if (P.depth && v) P.depth[seg] += v;
         }
     }

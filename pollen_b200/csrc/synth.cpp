@@ -156,4 +156,17 @@ int fgfa_synth_steps(int kind, uint32_t n_segs, uint32_t n_paths, const uint32_t
     return 0;
 }
 
+// One path of a graph, bit-identical to what fgfa_synth_steps writes for path `path_idx`
+// of a graph generated with `graph_seed` (paths are seeded individually): lets a rank
+// materialise only its shard.
+int fgfa_synth_path(int kind, uint32_t n_segs, uint64_t len, uint64_t graph_seed, uint32_t path_idx,
+                    uint32_t* out) {
+    if (n_segs == 0 || n_segs > 0x7FFFFFFFu) return -1;
+    const uint64_t pseed = graph_seed + path_idx;
+    if (kind == 0) gen_walk(out, len, n_segs, pseed);
+    else if (kind == 1) gen_skewed(out, len, n_segs, pseed, path_idx, graph_seed);
+    else gen_uniform(out, len, n_segs, pseed);
+    return 0;
+}
+
 }  // extern "C"

@@ -54,9 +54,13 @@ class ShardedDepth:
     """Per-rank engine: a DepthPlan over this rank's paths + the allreduce.
 
     ``local_start/local_end`` index the rank's packed local steps pool (see
-    ``pack_shard`` / ``synth.make_graph(path_subset=...)``)."""
+    ``pack_shard`` / ``synth.make_graph(path_subset=...)``).  ``n_paths_global`` is the
+    number of paths of the whole graph: when it is <= 255 the exchange uses u8 uniq
+    counters packed four to a word behind the u32 depths, so ONE allreduce moves
+    ``4*n_segs + n_segs`` bytes instead of ``8*n_segs`` (no byte can overflow because
+    ``uniq <= n_paths_global``)."""
 
-    def __init__(self, local_start, local_end, n_segs: int, device):
+    def __init__(self, local_start, local_end, n_segs: int, device, n_paths_global=None):
         import torch
 
         from .binding import DepthPlan
@@ -66,8 +70,15 @@ class ShardedDepth:
         self.n_segs = int(n_segs)
         self.n_local_steps = int(local_end[-1]) if len(local_end) else 0
         self.plan = DepthPlan(local_start, local_end, n_segs, self.n_local_steps)
-        # one buffer so that a single collective moves both arrays
-        self.out = torch.zeros(2 * self.n_segs, dtype=torch.int32, device=device)
+        self.compact = n_paths_global is not None and int(n_paths_global) <= 255
+        if self.compact:
+            self.plan.set_uniq_width(1)
+            self.out = torch.zeros(self.n_segs + (self.n_segs + 3) // 4, dtype=torch.int32, device=device)
+            self._uniq = self.out[self.n_segs:].view(torch.uint8)[: self.n_segs]
+        else:
+            # one buffer so that a single collective moves both arrays
+            self.out = torch.zeros(2 * self.n_segs, dtype=torch.int32, device=device)
+            self._uniq = self.out[self.n_segs:]
 
     @property
     def depth(self):
@@ -75,7 +86,21 @@ class ShardedDepth:
 
     @property
     def uniq(self):
-        return self.out[self.n_segs:]
+        """uint8 tensor in compact mode, int32 (u32 bit pattern) otherwise."""
+        return self._uniq
+
+    @property
+    def exchange_bytes(self) -> int:
+        return int(self.out.numel()) * 4
+
+    def results(self):
+        """(depth, uniq) as uint64 numpy arrays (downloads)."""
+        import numpy as np
+
+        d = self.depth.cpu().numpy().view(np.uint32).astype(np.uint64)
+        u = self.uniq.cpu().numpy()
+        u = (u if self.compact else u.view(np.uint32)).astype(np.uint64)
+        return d, u
 
     def run(self, d_steps, stream=None) -> None:
         """Enqueue: zero + kernels on this rank's shard, then the allreduce."""

@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
         h.fgfa_synth_spans.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
         h.fgfa_synth_steps.restype = C.c_int
         h.fgfa_synth_steps.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        h.fgfa_synth_path.restype = C.c_int
+        h.fgfa_synth_path.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
         _lib = h
     return _lib
 
@@ -91,22 +93,16 @@ def make_graph(cfg: Config, seed: int = SEED, out: np.ndarray | None = None, pat
     steps = out if out is not None else np.empty(total, dtype=np.uint32)
     new_end = np.cumsum(lens).astype(np.uint32)
     new_start = (new_end - lens).astype(np.uint32)
-    # per-path seeds are seed + original path index: generate one path at a time
+    # paths are seeded individually (seed + original path index): generate one at a time
     h = lib()
     threads = min(64, os.cpu_count() or 1)
     import concurrent.futures as cf
 
     def one(k):
-        p = int(idx[k])
-        s = np.array([new_start[k]], dtype=np.uint32)
-        e = np.array([new_end[k]], dtype=np.uint32)
-        # kind 1 needs the original path index for its window choice: seed is seed+p, path_idx 0
-        # would change the window, so generate through a 1-path call with an offset seed only
-        # for kinds whose output does not depend on the path index.
-        return h.fgfa_synth_steps(cfg.kind, cfg.n_segs, 1, s.ctypes.data, e.ctypes.data, seed + p, steps.ctypes.data, 1)
+        lo, hi = int(new_start[k]), int(new_end[k])
+        view = steps[lo:hi]
+        return h.fgfa_synth_path(cfg.kind, cfg.n_segs, hi - lo, seed, int(idx[k]), view.ctypes.data if hi > lo else None)
 
-    if cfg.kind == KIND_SKEWED:
-        raise NotImplementedError("path_subset generation is only offered for index-independent kinds")
     with cf.ThreadPoolExecutor(threads) as ex:
         for rc in ex.map(one, range(len(idx))):
             if rc:

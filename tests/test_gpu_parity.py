@@ -222,6 +222,37 @@ def test_plan_reuse_batches_and_feed_pipeline(torch_cuda):
         plan.close()
 
 
+@pytest.mark.parametrize("mode", ["direct", "window"])
+def test_both_seen_bit_strategies(torch_cuda, mode, monkeypatch):
+    """Kernel A's two ways of recording seen-bits (straight RED.OR per run / shared-memory
+    window flushed per bitmap sector) give identical results; the plan picks one by path
+    length, FGFA_SEEN_MODE forces it."""
+    torch = torch_cuda
+    monkeypatch.setenv("FGFA_SEEN_MODE", mode)
+    for name in ("tiny", "tinyE", "B"):
+        cfg = synth.CONFIGS[name]
+        steps, s, e = synth.make_graph(cfg)
+        rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+        plan = pb.DepthPlan(s, e, cfg.n_segs, cfg.n_steps)
+        d_steps = _dev(torch, steps)
+        out = torch.empty(2 * cfg.n_segs, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):
+            plan.run(d_steps, out[: cfg.n_segs], out[cfg.n_segs:], st)
+            plan.status(st)
+            g = out.cpu().numpy().view(np.uint32)
+            assert (g[: cfg.n_segs] == od).all() and (g[cfg.n_segs:] == ou).all(), (mode, name)
+        plan.close()
+    # a window-hostile graph: consecutive steps alternate between far-apart regions, so
+    # window slots collide and the fallback path is exercised
+    rng = np.random.default_rng(3)
+    n_segs = 3_000_000
+    a = rng.integers(0, 1000, 40_000, dtype=np.uint32)
+    segs = np.where(np.arange(40_000) % 2 == 0, a, a + 2_097_152 + 131_072 * (np.arange(40_000) % 5)).astype(np.uint32)
+    steps = (segs << 1).astype(np.uint32)
+    _check_vs_oracle(steps, np.array([0, 20_000], np.uint32), np.array([20_000, 40_000], np.uint32), n_segs)
+
+
 def test_misaligned_device_pointer_and_one_shot_device_abi(torch_cuda):
     torch = torch_cuda
     cfg = synth.CONFIGS["tiny"]
@@ -251,14 +282,26 @@ def test_sharded_partials_sum_to_the_whole(torch_cuda):
     steps, s, e = synth.make_graph(cfg)
     rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
     parts = sharding.lpt_partition(e - s, 4)
-    total = np.zeros(2 * cfg.n_segs, np.uint32)
-    for part in parts:
-        ls_steps, ls, le = synth.make_graph(cfg, path_subset=part)
-        eng = sharding.ShardedDepth(ls, le, cfg.n_segs, torch.device("cuda:0"))
-        eng.run(_dev(torch, ls_steps))
-        eng.status()
-        total += eng.out.cpu().numpy().view(np.uint32)
-    assert (total[: cfg.n_segs] == od).all() and (total[cfg.n_segs:] == ou).all()
+    for n_global in (None, cfg.n_paths):        # u32 exchange buffer / compact [depth u32 | uniq u8]
+        tot_d = np.zeros(cfg.n_segs, np.uint64)
+        tot_u = np.zeros(cfg.n_segs, np.uint64)
+        words = None
+        for part in parts:
+            ls_steps, ls, le = synth.make_graph(cfg, path_subset=part)
+            eng = sharding.ShardedDepth(ls, le, cfg.n_segs, torch.device("cuda:0"), n_paths_global=n_global)
+            assert eng.compact == (n_global is not None)
+            eng.run(_dev(torch, ls_steps))
+            eng.status()
+            d, u = eng.results()
+            tot_d += d
+            tot_u += u
+            w = eng.out.cpu().numpy().view(np.uint32).astype(np.uint64)
+            words = w if words is None else words + w     # what the allreduce would compute
+        assert (tot_d == od).all() and (tot_u == ou).all()
+        assert (words[: cfg.n_segs] == od).all()
+        if n_global is not None:                            # packed bytes never carry
+            packed = words[cfg.n_segs:].astype(np.uint32).view(np.uint8)[: cfg.n_segs]
+            assert (packed == ou).all()
 
 
 # ------------------------------------------------------------------- full size ------

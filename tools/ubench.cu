@@ -210,12 +210,14 @@ int main(int argc, char** argv) {
         }
         time_it("depth-only half-lanes(seg even) g=8xSM", [&] { k_step_stream_direct<kModeDepthHalfLanes, 1><<<sms * 8, kThreads>>>(P); }, false);
         time_it("depth-only pairs(+2 even tid) g=8xSM", [&] { k_step_stream_direct<kModeDepthPairs, 1><<<sms * 8, kThreads>>>(P); }, false);
-        time_it("merged depth+seen g=4xSM", [&] { k_step_stream_merged<4, true><<<sms * 4, kThreads>>>(S); }, true);
-        time_it("merged depth+seen g=6xSM", [&] { k_step_stream_merged<6, true><<<sms * 6, kThreads>>>(S); }, true);
-        time_it("merged depth+seen g=5xSM", [&] { k_step_stream_merged<5, true><<<sms * 5, kThreads>>>(S); }, true);
-        time_it("merged depth+seen g=6x2", [&] { k_step_stream_merged<6, true><<<sms * 12, kThreads>>>(S); }, true);
-        time_it("merged depth+seen g=8xSM", [&] { k_step_stream_merged<8, true><<<sms * 8, kThreads>>>(S); }, true);
-        time_it("merged depth-only g=8xSM", [&] { k_step_stream_merged<8, false><<<sms * 8, kThreads>>>(S); }, true);
+        const size_t smD = stream_smem_bytes(kSeenDirect), smW = stream_smem_bytes(kSeenWindow);
+        CK(cudaFuncSetAttribute(k_step_stream_merged<8, kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smW));
+        CK(cudaFuncSetAttribute(k_step_stream_merged<4, kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smW));
+        time_it("merged direct-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenDirect><<<sms * 4, kThreads, smD>>>(S); }, true);
+        time_it("merged direct-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenDirect><<<sms * 8, kThreads, smD>>>(S); }, true);
+        time_it("merged window-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenWindow><<<sms * 4, kThreads, smW>>>(S); }, true);
+        time_it("merged window-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenWindow><<<sms * 8, kThreads, smW>>>(S); }, true);
+        time_it("merged depth-only g=8xSM", [&] { k_step_stream_merged<8, kSeenNone><<<sms * 8, kThreads, smD>>>(S); }, true);
         time_it("warp-agg A only g=4xSM", [&] { k_step_stream_warp_agg<4><<<sms * 4, kThreads>>>(P); }, true);
         time_it("warp-agg A only g=6xSM", [&] { k_step_stream_warp_agg<6><<<sms * 6, kThreads>>>(P); }, true);
         time_it("warp-agg A only g=8xSM", [&] { k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); }, true);
@@ -230,7 +232,7 @@ int main(int argc, char** argv) {
             for (int r = 0; r < reps + 2; ++r) {
                 CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
-                if (use_merged) k_step_stream_merged<8, true><<<sms * 8, kThreads>>>(S); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
+                if (use_merged) k_step_stream_merged<8, kSeenWindow><<<sms * 8, kThreads, stream_smem_bytes(kSeenWindow)>>>(S); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
                 k_uniq_popcount<<<pgrid, kPopThreads>>>(Q2);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
