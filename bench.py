@@ -201,17 +201,18 @@ def main():
     for a, b in probes:            # torch creates the CUDA event lazily, on first record
         a.record(stream)
         b.record(stream)
+    # clocks are sampled from here to the end of the e2e measurement (the timed region alone
+    # lasts ~15 ms, shorter than one nvidia-smi poll)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
     if sampler:
         sampler.start()
+    barrier()
     ev0.record(stream)
     for k in range(args.steps):
         eng.plan.set_probe(probes[k][0].cuda_event, probes[k][1].cuda_event)
         eng.run(d_steps, stream)
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop() if sampler else None
     eng.status()
     ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     ms_kernel = torch.tensor([statistics.mean(a.elapsed_time(b) for a, b in probes)], dtype=torch.float64, device=dev)
@@ -310,6 +311,8 @@ def main():
         e2e_api = "ShardedDepth.run on pinned host shards (H2D + kernels + NCCL allreduce + D2H)"
     e2e = {"value": cfg.n_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local + 8 * len(my_paths),
            "d2h_bytes_per_step": eng.exchange_bytes if world > 1 else 8 * cfg.n_segs, "ms_per_step": e2e_s * 1e3, "api": e2e_api, "steps": e2e_steps}
+
+    clocks = sampler.stop() if sampler else None
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------
     cpu = None

@@ -93,6 +93,16 @@ int fgfa_depth_plan_status(fgfa_depth_plan_t* plan, void* cuda_stream);
  * packed bytes can be summed as u32 words because no global uniq exceeds 255 either. */
 int fgfa_depth_plan_set_uniq_width(fgfa_depth_plan_t* plan, int bytes);
 
+/* Path-depth mode (`path_depth` + `measure_path`, depth.rs:88-131) on device buffers.
+ * d_depth: the n_segs u32 depths of a previous run over ALL paths (depth.rs:93-99);
+ * d_seg_len: n_segs u32 sequence lengths (`Segment::len`, flatgfa.rs:84-89);
+ * d_scratch: 8*n_segs bytes; d_sums: 2*n_paths u64, receives for every path p
+ * sums[2p] = sum(depth[seg]*len(seg)) and sums[2p+1] = sum(len(seg)) over its steps
+ * (wrapping u64, like usize).  mean depth = sums[2p] / sums[2p+1] as f64 (depth.rs:129). */
+int fgfa_depth_plan_path_sums(fgfa_depth_plan_t* plan, const uint32_t* d_steps, const uint32_t* d_depth,
+                              const uint32_t* d_seg_len, void* d_scratch, uint64_t* d_sums,
+                              void* cuda_stream);
+
 /* Measurement hook: the next fgfa_depth_plan_run/feed records `before` immediately
  * before and `after` immediately after its step-stream kernel launches (CUDA events
  * owned by the caller, timing enabled).  Pass NULLs to clear.  One-shot: cleared after
@@ -118,6 +128,16 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
                                    const uint32_t* h_span_start, const uint32_t* h_span_end,
                                    uint32_t n_paths, uint32_t n_segs, uint64_t* depth_out,
                                    uint64_t* uniq_out);
+
+/* path_depth over host arrays (depth.rs:88-113): node depth over ALL paths, then for each
+ * queried path id its length in base pairs and its mean depth.  h_seg_len: n_segs u32
+ * sequence lengths.  path_ids may be NULL = all paths in order (`gfa.paths.ids()`).
+ * length_out, weighted_out (sum of depth*len, exact) and mean_out have n_query entries;
+ * weighted_out may be NULL. */
+int fgfa_path_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint32_t* h_span_start,
+                          const uint32_t* h_span_end, uint32_t n_paths, const uint32_t* h_seg_len,
+                          uint32_t n_segs, const uint32_t* path_ids, uint32_t n_query,
+                          uint64_t* length_out, uint64_t* weighted_out, double* mean_out);
 
 /* The host-buffer entry points keep their device/pinned staging and the last plan in a
  * process-wide workspace between calls; this frees it (it is re-created on demand).

@@ -8,7 +8,9 @@
  *
  * Parity pinning: the Rust reference cannot be built here (no cargo/rustc, crates
  * not vendored), so this restatement is pinned against (a) the reference's in-repo
- * golden tables for the path (slow_odgi/README.md:147-175, flatgfa-sh/README.md:31-36)
+ * golden table for the path (slow_odgi/README.md:147-175; the second documented table,
+ * flatgfa-sh/README.md:31-36, needs note5.gfa which the reference fetches from odgi at
+ * test time and is therefore not usable offline)
  * and (b) outputs of the reference's own Python implementation `slow_odgi depth`
  * (slow_odgi/slow_odgi/depth.py:6-16) run in the build container on the reference's
  * fixtures and on seeded random graphs; those outputs are committed under
@@ -167,4 +169,49 @@ int oracle_file_seg_names(const uint8_t* data, uint64_t len, uint64_t* names) {
     if (rc) return rc;
     for (uint64_t i = 0; i < v.n_segs; ++i) names[i] = rd64(data + v.segs_off + 24 * i);
     return 0;
+}
+
+/*
+ * flatgfa/src/ops/depth.rs:88-113 path_depth + :116-131 measure_path ("next" row).
+ * Node depth over ALL paths (depth.rs:93-99), then for each queried path id the length in
+ * base pairs and the mean depth weighted by segment length.  `seg_len[i]` is Segment::len
+ * (flatgfa.rs:84-89).  usize arithmetic wraps (release build), the divide is f64.
+ * PARITY UNPINNED for this function: the reference repository holds no runnable golden
+ * for path depth (slow_odgi has no path mode; the tables in flatgfa-sh/README.md:57-59,
+ * 267-270 need note5.gfa / k.gfa, which are fetched from odgi at test time).
+ */
+int oracle_path_depth(const uint32_t* steps, uint64_t n_steps, const uint32_t* spans, uint32_t n_paths,
+                      const uint32_t* seg_len, uint32_t n_segs, const uint32_t* path_ids,
+                      uint32_t n_query, uint64_t* lengths, double* means) {
+    uint64_t* seg_depths = (uint64_t*)malloc((size_t)(n_segs ? n_segs : 1) * sizeof(uint64_t));
+    if (!seg_depths) return -2;
+    int rc = oracle_seg_depth(steps, n_steps, spans, n_paths, n_segs, seg_depths);
+    if (rc) { free(seg_depths); return rc; }
+    for (uint32_t q = 0; q < n_query; ++q) {           /* depth.rs:104-108 */
+        uint32_t p = path_ids ? path_ids[q] : q;
+        if (p >= n_paths) { free(seg_depths); return -1; }
+        uint64_t depth = 0, length = 0;                /* depth.rs:121-122 */
+        for (uint32_t i = spans[2 * p]; i < spans[2 * p + 1]; ++i) {
+            uint32_t seg = handle_segment(steps[i]);
+            uint64_t len = seg_len[seg];               /* depth.rs:125 */
+            depth += seg_depths[seg] * len;            /* depth.rs:126 */
+            length += len;                             /* depth.rs:127 */
+        }
+        lengths[q] = length;
+        means[q] = (double)depth / (double)length;     /* depth.rs:129 */
+    }
+    free(seg_depths);
+    return 0;
+}
+
+/* depth.rs:192-197 format_float: "{:.digits$}", trim trailing '0', then a trailing '.'. */
+int oracle_format_float(double x, int digits, char* out, size_t cap) {
+    if (x != x) return snprintf(out, cap, "NaN");      /* Rust prints f64 NaN as "NaN" */
+    if (x > 1.7976931348623157e308) return snprintf(out, cap, "inf");
+    if (x < -1.7976931348623157e308) return snprintf(out, cap, "-inf");
+    int n = snprintf(out, cap, "%.*f", digits, x);
+    if (n < 0 || (size_t)n >= cap) return -1;
+    while (n > 0 && out[n - 1] == '0') out[--n] = 0;
+    while (n > 0 && out[n - 1] == '.') out[--n] = 0;
+    return n;
 }

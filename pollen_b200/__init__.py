@@ -14,6 +14,7 @@ from .binding import (  # noqa: F401
     SegDepth,
     device_count,
     lib,
+    path_depth_steps,
     seg_depth,
     seg_depth_steps,
     seg_depth_with_uniq,
@@ -27,6 +28,7 @@ __all__ = [
     "SegDepth",
     "device_count",
     "lib",
+    "path_depth_steps",
     "seg_depth",
     "seg_depth_steps",
     "seg_depth_with_uniq",

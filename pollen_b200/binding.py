@@ -60,6 +60,8 @@ EXPORTS = {
     "flatgfa_load": (C.c_void_p, [C.c_char_p]),
     "flatgfa_seg_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "flatgfa_format_seg_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "flatgfa_path_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "flatgfa_format_path_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "flatgfa_dump": (C.c_int, [C.c_void_p, C.c_char_p]),
     "flatgfa_last_error": (C.c_char_p, []),
     # include/fgfa_depth.h
@@ -80,6 +82,8 @@ EXPORTS = {
     "fgfa_depth_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_seg_depth_with_uniq_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fgfa_release_workspace": (None, []),
+    "fgfa_path_depth_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_path_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_flatgfa_counts": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fgfa_seg_depth_with_uniq": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "fgfa_seg_depth": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -133,6 +137,25 @@ def seg_depth_with_uniq_steps(steps, span_start, span_end, n_segs: int, want_uni
         )
     )
     return depth, uniq
+
+
+def path_depth_steps(steps, span_start, span_end, seg_len, path_ids=None):
+    """path_depth (depth.rs:88-113) over raw host arrays.  Returns (lengths u64, weighted
+    sums u64, mean depths f64) for the queried path ids (default: all paths in order)."""
+    steps, span_start, span_end, seg_len = _u32(steps), _u32(span_start), _u32(span_end), _u32(seg_len)
+    ids = None if path_ids is None else _u32(path_ids)
+    n = span_start.size if ids is None else ids.size
+    lengths = np.empty(n, dtype=np.uint64)
+    weighted = np.empty(n, dtype=np.uint64)
+    means = np.empty(n, dtype=np.float64)
+    _check(
+        lib().fgfa_path_depth_steps(
+            steps.ctypes.data, steps.size, span_start.ctypes.data, span_end.ctypes.data, span_start.size,
+            seg_len.ctypes.data, seg_len.size, None if ids is None else ids.ctypes.data, n,
+            lengths.ctypes.data, weighted.ctypes.data, means.ctypes.data,
+        )
+    )
+    return lengths, weighted, means
 
 
 def seg_depth_steps(steps, span_start, span_end, n_segs: int) -> np.ndarray:
@@ -211,6 +234,27 @@ class FlatGFA:
         depth = np.empty(self.segment_count, dtype=np.uint64)
         _check(lib().flatgfa_seg_depth(self._h, depth.ctypes.data, None))
         return depth
+
+    def path_depth(self, path_ids=None):
+        """``ops::depth::path_depth`` (depth.rs:88-113): (lengths u64, mean depths f64)."""
+        ids = None if path_ids is None else _u32(path_ids)
+        n = self.path_count if ids is None else int(ids.size)
+        lengths = np.empty(n, dtype=np.uint64)
+        means = np.empty(n, dtype=np.float64)
+        _check(lib().flatgfa_path_depth(self._h, None if ids is None else ids.ctypes.data, n, lengths.ctypes.data, means.ctypes.data))
+        return lengths, means
+
+    def format_path_depth(self, lengths, means, path_ids=None) -> bytes:
+        ids = None if path_ids is None else _u32(path_ids)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+        means = np.ascontiguousarray(means, dtype=np.float64)
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().flatgfa_format_path_depth(self._h, None if ids is None else ids.ctypes.data, lengths.size,
+                                               lengths.ctypes.data, means.ctypes.data, C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            C.CDLL(None).free(out)
 
     def format_seg_depth(self, depth: np.ndarray, uniq: np.ndarray) -> bytes:
         depth = np.ascontiguousarray(depth, dtype=np.uint64)

@@ -149,6 +149,50 @@ int flatgfa_format_seg_depth(flatgfa_t gfa, const uint64_t* depth, const uint64_
     return FGFA_OK;
 }
 
+int flatgfa_path_depth(flatgfa_t gfa, const uint32_t* path_ids, uint32_t n, uint64_t* lengths,
+                       double* mean_depths) {
+    if (!gfa || (n && (!lengths || !mean_depths))) return FGFA_ERR_INVALID_ARG;
+    try {
+        std::vector<uint32_t> ids(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            ids[i] = path_ids ? path_ids[i] : i;
+            if (ids[i] >= gfa->gfa.paths.len()) return FGFA_ERR_INVALID_ARG;
+        }
+        auto ld = flatgfa::ops::depth::path_depth(gfa->gfa, ids);
+        for (uint32_t i = 0; i < n; ++i) { lengths[i] = ld.first[i]; mean_depths[i] = ld.second[i]; }
+        return FGFA_OK;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return std::strstr(e.what(), "no CUDA device") ? FGFA_ERR_NO_DEVICE : FGFA_ERR_CUDA;
+    }
+}
+
+int flatgfa_format_path_depth(flatgfa_t gfa, const uint32_t* path_ids, uint32_t n, const uint64_t* lengths,
+                              const double* mean_depths, char** out, size_t* out_len) {
+    if (!gfa || !out || !out_len || (n && (!lengths || !mean_depths))) return FGFA_ERR_INVALID_ARG;
+    std::vector<uint32_t> ids(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        ids[i] = path_ids ? path_ids[i] : i;
+        if (ids[i] >= gfa->gfa.paths.len()) return FGFA_ERR_INVALID_ARG;
+    }
+    flatgfa::ops::depth::PathDepth t{gfa->gfa, std::vector<uint64_t>(lengths, lengths + n),
+                                     std::vector<double>(mean_depths, mean_depths + n), ids};
+    std::string s;
+    try {
+        t.emit(s);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return FGFA_ERR_INVALID_ARG;
+    }
+    char* buf = static_cast<char*>(std::malloc(s.size() + 1));
+    if (!buf) return FGFA_ERR_NOMEM;
+    std::memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+    *out = buf;
+    *out_len = s.size();
+    return FGFA_OK;
+}
+
 int flatgfa_dump(flatgfa_t gfa, const char* filename) {
     if (!gfa || !filename) return FGFA_ERR_INVALID_ARG;
     try {

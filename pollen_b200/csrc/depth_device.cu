@@ -353,6 +353,36 @@ int fgfa_depth_plan_set_probe(fgfa_depth_plan_t* pl, void* before, void* after) 
     return FGFA_OK;
 }
 
+int fgfa_depth_plan_path_sums(fgfa_depth_plan_t* pl, const uint32_t* d_steps, const uint32_t* d_depth,
+                              const uint32_t* d_seg_len, void* d_scratch, uint64_t* d_sums,
+                              void* cuda_stream) {
+    if (!pl || !d_sums || (pl->n_segs && (!d_depth || !d_seg_len || !d_scratch)))
+        return fail(FGFA_ERR_INVALID_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU(cudaMemsetAsync(d_sums, 0, (size_t)pl->n_paths * 16, st));
+    const uint32_t chunks = pl->h_prefix[pl->n_paths];
+    if (chunks == 0) return FGFA_OK;
+    const uint32_t* base = d_steps;
+    int rc = prepare_pointer(pl, d_steps, &base);
+    if (rc) return rc;
+    uint2* dl = static_cast<uint2*>(d_scratch);
+    fgfa::k_interleave_depth_len<<<(pl->n_segs + 255) / 256, 256, 0, st>>>(d_depth, d_seg_len, dl, pl->n_segs);
+    CU(cudaGetLastError());
+    fgfa::MeasureParams M{};
+    M.steps = base;
+    M.chunks = pl->d_chunks;
+    M.chunk_lo = 0;
+    M.chunk_hi = chunks;
+    M.n_segs = pl->n_segs;
+    M.depth_len = dl;
+    M.sums = reinterpret_cast<unsigned long long*>(d_sums);
+    M.err = pl->d_err;
+    const uint32_t grid = std::min<uint32_t>(chunks, (uint32_t)pl->sms * 8);
+    fgfa::k_path_measure<<<grid, fgfa::kThreads, 0, st>>>(M);
+    CU(cudaGetLastError());
+    return FGFA_OK;
+}
+
 uint32_t fgfa_depth_plan_launches(const fgfa_depth_plan_t* pl, int with_uniq) {
     if (!pl || pl->n_paths == 0) return 0;
     const uint32_t batches = (pl->n_paths + pl->rows_per_batch - 1) / pl->rows_per_batch;

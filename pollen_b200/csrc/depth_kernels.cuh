@@ -387,4 +387,72 @@ __global__ void __launch_bounds__(kPopThreads) k_uniq_popcount(PopcountParams P)
     }
 }
 
+// ---------------------------------------------------------------------------
+// kernel C (k_path_measure): the per-path weighted sums of the reference's path-depth mode,
+//   sums[2p]   = sum over the steps of path p of depth[seg] * len(seg)     (depth.rs:122-123)
+//   sums[2p+1] = sum over the steps of path p of len(seg)                  (depth.rs:124)
+// (`measure_path`, flatgfa/src/ops/depth.rs:116-131; the one f64 divide is done on the host).
+// A gather + segmented reduction: steps are streamed in lane order (coalesced), the
+// interleaved {depth, len} table (8 bytes per segment, L2-resident) is gathered once per
+// step, every CTA reduces its chunk to two u64 and adds them to its path's accumulators.
+// Arithmetic is wrapping u64, like `usize` in a release build of the reference.
+// ---------------------------------------------------------------------------
+struct MeasureParams {
+    const uint32_t* __restrict__ steps;
+    const ChunkDesc* __restrict__ chunks;
+    uint32_t chunk_lo, chunk_hi;
+    uint32_t n_segs;
+    const uint2* __restrict__ depth_len;          // [n_segs] {depth, len}
+    unsigned long long* __restrict__ sums;        // [2 * n_paths], zero on entry
+    uint32_t* __restrict__ err;
+};
+
+__global__ void __launch_bounds__(256) k_interleave_depth_len(const uint32_t* __restrict__ depth,
+                                                              const uint32_t* __restrict__ len,
+                                                              uint2* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_uint2(depth[i], len[i]);
+}
+
+__global__ void __launch_bounds__(kThreads) k_path_measure(MeasureParams P) {
+    __shared__ unsigned long long s_part[2][kThreads / 32];
+    const uint64_t pol = make_evict_first_policy();
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t c = P.chunk_lo + blockIdx.x; c < P.chunk_hi; c += gridDim.x) {
+        const ChunkDesc d = P.chunks[c];
+        uint32_t h[kItems];
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const uint64_t idx = (uint64_t)d.a + (uint64_t)i * kThreads + tid;
+            h[i] = (idx >= d.s && idx < d.e) ? ld_stream_u32(P.steps + idx, pol) : kFiller;
+        }
+        unsigned long long wsum = 0, lsum = 0;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const uint32_t seg = h[i] >> 1;
+            if (seg < P.n_segs) {
+                const uint2 dl = __ldg(P.depth_len + seg);
+                wsum += (unsigned long long)dl.x * dl.y;
+                lsum += dl.y;
+            } else if (h[i] != kFiller) {
+                *P.err = 1u;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
+            lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+        }
+        if (lane == 0) { s_part[0][warp] = wsum; s_part[1][warp] = lsum; }
+        __syncthreads();
+        if (tid < 2) {
+            unsigned long long t = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) t += s_part[tid][w];
+            atomicAdd(P.sums + 2 * (size_t)d.path + tid, t);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace fgfa

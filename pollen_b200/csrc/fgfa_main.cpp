@@ -4,6 +4,7 @@
 // flatgfa/src/cli/cmds.rs:217-232 `depth` options, main.rs:87-138 input loading and
 // dispatch, main.rs:190-213 `dump`):
 //   fgfa [-i FLATGFA | -I GFA | < GFA] depth -d          node-depth table on stdout
+//   fgfa [-i FLATGFA | -I GFA | < GFA] depth [-r PATH]   path-depth table (cmds.rs:256-283)
 //   fgfa [-i FLATGFA | -I GFA | < GFA] -o OUT.flatgfa    convert to the binary format
 // The other thirteen subcommands of the reference are outside this repository's scope
 // and are rejected with an error.
@@ -100,9 +101,28 @@ int main(int argc, char** argv) {
         }
 
         if (a.command == "depth") {                                           // main.rs:136-138
-            if (!a.seg_depth) {
-                std::fprintf(stderr, "fgfa depth: only the node-depth table (-d) is implemented in this build\n");
+            if (!a.seg_depth && !a.bed.empty()) {
+                std::fprintf(stderr, "fgfa depth: BED interval mode (-b) is outside the scope of this build\n");
                 return 1;
+            }
+            if (!a.seg_depth) {                                               // cmds.rs:256-283: path depth table
+                std::vector<uint32_t> ids;
+                if (a.paths.empty()) {
+                    for (size_t p = 0; p < gfa.paths.len(); ++p) ids.push_back((uint32_t)p);   // gfa.paths.ids()
+                } else {
+                    for (const auto& name : a.paths) {                        // find_path (flatgfa.rs:376-378); unknown names are dropped
+                        for (size_t p = 0; p < gfa.paths.len(); ++p) {
+                            const auto nm = gfa.get_path_name(gfa.paths[p]);
+                            if (nm.len() == name.size() && std::memcmp(nm.data, name.data(), name.size()) == 0) {
+                                ids.push_back((uint32_t)p);
+                                break;
+                            }
+                        }
+                    }
+                }
+                auto ld = flatgfa::ops::depth::path_depth(gfa, ids);
+                flatgfa::ops::depth::PathDepth{gfa, std::move(ld.first), std::move(ld.second), ids}.print();
+                return 0;
             }
             auto du = flatgfa::ops::depth::seg_depth_with_uniq(gfa);          // cmds.rs:239
             flatgfa::ops::depth::SegDepth{gfa, std::move(du.first), std::move(du.second)}.print();  // cmds.rs:240-245

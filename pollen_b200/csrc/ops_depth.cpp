@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -26,6 +27,7 @@ struct Workspace {
     uint32_t* steps = nullptr;  size_t steps_cap = 0;     // elements
     uint32_t* out = nullptr;    size_t out_cap = 0;       // elements ([depth | uniq])
     uint32_t* h_out = nullptr;  size_t h_out_cap = 0;     // pinned, elements
+    void* aux = nullptr;        size_t aux_cap = 0;       // bytes (path-depth scratch)
     cudaStream_t copy = nullptr, compute = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     fgfa_depth_plan_t* plan = nullptr;
@@ -38,6 +40,7 @@ struct Workspace {
         cudaFree(out); out = nullptr; out_cap = 0;
         if (h_out) cudaFreeHost(h_out);
         h_out = nullptr; h_out_cap = 0;
+        cudaFree(aux); aux = nullptr; aux_cap = 0;
         for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
         if (copy) cudaStreamDestroy(copy);
         if (compute) cudaStreamDestroy(compute);
@@ -62,7 +65,7 @@ uint64_t fnv1a(const uint32_t* a, size_t n, uint64_t h) {
     return h;
 }
 
-int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, bool want_uniq) {
+int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, bool want_uniq, size_t aux_bytes = 0) {
     int dev = 0;
     CUH(cudaGetDevice(&dev));
     if (w.device != dev) {
@@ -90,6 +93,11 @@ int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, bool want_
         w.h_out = nullptr; w.h_out_cap = 0;
         CUH(cudaMallocHost(&w.h_out, need_out * 4));
         w.h_out_cap = need_out;
+    }
+    if (w.aux_cap < aux_bytes) {
+        cudaFree(w.aux); w.aux = nullptr; w.aux_cap = 0;
+        CUH(cudaMalloc(&w.aux, aux_bytes));
+        w.aux_cap = aux_bytes;
     }
     (void)want_uniq;
     return FGFA_OK;
@@ -183,6 +191,60 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
     CUH(cudaStreamSynchronize(W.copy));
     widen(W.h_out, depth_out, n_segs);
     if (want_uniq) widen(W.h_out + n_segs, uniq_out, n_segs);
+    return FGFA_OK;
+}
+
+int fgfa_path_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint32_t* h_span_start,
+                          const uint32_t* h_span_end, uint32_t n_paths, const uint32_t* h_seg_len,
+                          uint32_t n_segs, const uint32_t* path_ids, uint32_t n_query,
+                          uint64_t* length_out, uint64_t* weighted_out, double* mean_out) {
+    if ((n_steps && !h_steps) || (n_paths && (!h_span_start || !h_span_end)) || (n_segs && !h_seg_len) ||
+        (n_query && (!length_out || !mean_out)))
+        return FGFA_ERR_INVALID_ARG;
+    if (path_ids)
+        for (uint32_t q = 0; q < n_query; ++q)
+            if (path_ids[q] >= n_paths) return FGFA_ERR_INVALID_ARG;
+    if (!path_ids && n_query != n_paths) return FGFA_ERR_INVALID_ARG;
+    if (fgfa_device_count() <= 0) return FGFA_ERR_NO_DEVICE;
+    Workspace& W = g_ws;
+    std::lock_guard<std::mutex> lock(W.mu);
+    const char* env = std::getenv("FGFA_WORKSPACE");
+    const bool keep = !(env && env[0] == '0');
+    struct Releaser { Workspace& w; bool on; ~Releaser() { if (on) w.release(); } } releaser{W, !keep};
+
+    const size_t sums_bytes = std::max<size_t>((size_t)n_paths * 16, 16);
+    const size_t scratch_bytes = std::max<size_t>((size_t)n_segs * 8, 16);
+    int rc = ensure_workspace(W, n_steps, n_segs, false, scratch_bytes + sums_bytes);
+    if (rc) return rc;
+    const uint64_t key[4] = {n_paths, n_segs, n_steps,
+                             fnv1a(h_span_end, n_paths, fnv1a(h_span_start, n_paths, 0xCBF29CE484222325ull))};
+    if (!W.plan || std::memcmp(key, W.plan_key, sizeof key) != 0) {
+        if (W.plan) fgfa_depth_plan_destroy(W.plan);
+        W.plan = nullptr;
+        rc = fgfa_depth_plan_create(&W.plan, h_span_start, h_span_end, n_paths, n_segs, n_steps, 0);
+        if (rc) return rc;
+        std::memcpy(W.plan_key, key, sizeof key);
+    }
+    uint32_t* d_depth = W.out;
+    uint32_t* d_len = W.out + n_segs;
+    uint64_t* d_sums = reinterpret_cast<uint64_t*>(static_cast<char*>(W.aux) + scratch_bytes);
+    if (n_steps) CUH(cudaMemcpyAsync(W.steps, h_steps, (size_t)n_steps * 4, cudaMemcpyHostToDevice, W.compute));
+    if (n_segs) CUH(cudaMemcpyAsync(d_len, h_seg_len, (size_t)n_segs * 4, cudaMemcpyHostToDevice, W.compute));
+    rc = fgfa_depth_plan_run(W.plan, W.steps, d_depth, nullptr, W.compute);          // depth.rs:93-99
+    if (rc) return rc;
+    rc = fgfa_depth_plan_path_sums(W.plan, W.steps, d_depth, d_len, W.aux, d_sums, W.compute);
+    if (rc) return rc;
+    std::vector<uint64_t> sums((size_t)n_paths * 2);
+    if (n_paths) CUH(cudaMemcpyAsync(sums.data(), d_sums, (size_t)n_paths * 16, cudaMemcpyDeviceToHost, W.compute));
+    rc = fgfa_depth_plan_status(W.plan, W.compute);
+    if (rc) return rc;
+    for (uint32_t q = 0; q < n_query; ++q) {
+        const uint32_t p = path_ids ? path_ids[q] : q;
+        const uint64_t weighted = sums[2 * (size_t)p], length = sums[2 * (size_t)p + 1];
+        length_out[q] = length;
+        if (weighted_out) weighted_out[q] = weighted;
+        mean_out[q] = (double)weighted / (double)length;                              // depth.rs:129
+    }
     return FGFA_OK;
 }
 
@@ -291,6 +353,64 @@ std::vector<uint64_t> seg_depth(const FlatGFA& gfa) {
     int rc = run_on(gfa, d, nullptr);
     if (rc) raise(rc);
     return d;
+}
+
+std::pair<std::vector<uint64_t>, std::vector<double>> path_depth(const FlatGFA& gfa,
+                                                                 const std::vector<uint32_t>& paths) {
+    if (gfa.segs.len() > 0x7FFFFFFFull || gfa.paths.len() > 0xFFFFFFFFull || gfa.steps.len() > 0xFFFFFFFFull)
+        raise(FGFA_ERR_TOO_LARGE);
+    const uint32_t n_paths = (uint32_t)gfa.paths.len(), n_segs = (uint32_t)gfa.segs.len();
+    std::vector<uint32_t> s(n_paths), e(n_paths), len(n_segs);
+    for (uint32_t p = 0; p < n_paths; ++p) {
+        s[p] = gfa.paths.data[p].steps.start;
+        e[p] = gfa.paths.data[p].steps.end;
+    }
+    for (uint32_t i = 0; i < n_segs; ++i) len[i] = (uint32_t)gfa.segs.data[i].len();   // flatgfa.rs:84-89
+    const uint32_t* steps = reinterpret_cast<const uint32_t*>(gfa.steps.data);
+    std::vector<uint32_t> aligned;
+    if (reinterpret_cast<uintptr_t>(steps) & 3u) {
+        aligned.resize(gfa.steps.len());
+        std::memcpy(aligned.data(), gfa.steps.data, gfa.steps.len() * 4);
+        steps = aligned.data();
+    }
+    std::vector<uint64_t> lengths(paths.size());
+    std::vector<double> depths(paths.size());
+    int rc = fgfa_path_depth_steps(steps, gfa.steps.len(), s.data(), e.data(), n_paths, len.data(), n_segs,
+                                   paths.data(), (uint32_t)paths.size(), lengths.data(), nullptr, depths.data());
+    if (rc) raise(rc);
+    return {std::move(lengths), std::move(depths)};
+}
+
+// depth.rs:192-197: `{:.digits$}` then trim trailing zeroes, then a trailing '.'.
+std::string format_float(double x, int digits) {
+    if (x != x) return "NaN";                                  // Rust's Display for f64
+    if (x == std::numeric_limits<double>::infinity()) return "inf";
+    if (x == -std::numeric_limits<double>::infinity()) return "-inf";
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "%.*f", digits, x);
+    std::string s(buf);
+    while (!s.empty() && s.back() == '0') s.pop_back();
+    while (!s.empty() && s.back() == '.') s.pop_back();
+    return s;
+}
+
+void PathDepth::emit(std::string& out) const {
+    out += "#path\tstart\tend\tmean.depth\n";                              // depth.rs:148
+    for (size_t i = 0; i < paths.size(); ++i) {                            // depth.rs:149-157
+        const Pool<uint8_t> name = gfa.get_path_name(gfa.paths[paths[i]]);
+        out.append(reinterpret_cast<const char*>(name.data), name.len());
+        out += "\t0\t";
+        out += std::to_string(lengths[i]);
+        out += '\t';
+        out += format_float(depths[i], 2);
+        out += '\n';
+    }
+}
+
+void PathDepth::emit(FILE* f) const {
+    std::string s;
+    emit(s);
+    std::fwrite(s.data(), 1, s.size(), f);
 }
 
 namespace {

@@ -35,6 +35,25 @@ struct SegDepth {
     void print() const { emit(stdout); }   // emit.rs:13-18
 };
 
+// depth.rs:88-113: node depth over ALL paths, then (length in bp, mean depth) of each
+// queried path.  `paths` are path pool indices (the reference takes an iterator of ids).
+std::pair<std::vector<uint64_t>, std::vector<double>> path_depth(const FlatGFA& gfa,
+                                                                 const std::vector<uint32_t>& paths);
+
+// depth.rs:192-197.
+std::string format_float(double x, int digits);
+
+// depth.rs:136-160: the odgi-style path-depth TSV.
+struct PathDepth {
+    const FlatGFA& gfa;
+    std::vector<uint64_t> lengths;
+    std::vector<double> depths;
+    std::vector<uint32_t> paths;
+    void emit(std::string& out) const;
+    void emit(FILE* f) const;
+    void print() const { emit(stdout); }
+};
+
 }  // namespace depth
 }  // namespace ops
 }  // namespace flatgfa

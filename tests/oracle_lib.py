@@ -26,6 +26,11 @@ def oracle():
         h.oracle_emit_seg_depth.restype = C.c_int64
         h.oracle_emit_seg_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint64]
 
+        h.oracle_path_depth.restype = C.c_int
+        h.oracle_path_depth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        h.oracle_format_float.restype = C.c_int
+        h.oracle_format_float.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_size_t]
+
         class View(C.Structure):
             _fields_ = [(n, C.c_uint64) for n in ("n_segs", "n_paths", "n_steps", "segs_off", "paths_off", "steps_off")]
 
@@ -59,6 +64,36 @@ def depth_only(steps, start, end, n_segs):
     d = np.empty(n_segs, dtype=np.uint64)
     rc = oracle().oracle_seg_depth(steps.ctypes.data, steps.size, sp.ctypes.data, len(start), n_segs, d.ctypes.data)
     return rc, d
+
+
+def path_depth(steps, start, end, seg_len, path_ids=None):
+    """oracle_path_depth -> (rc, lengths u64, means f64)."""
+    steps = np.ascontiguousarray(steps, dtype=np.uint32)
+    seg_len = np.ascontiguousarray(seg_len, dtype=np.uint32)
+    sp = spans_of(start, end)
+    ids = None if path_ids is None else np.ascontiguousarray(path_ids, dtype=np.uint32)
+    n = len(start) if ids is None else ids.size
+    lengths = np.empty(n, dtype=np.uint64)
+    means = np.empty(n, dtype=np.float64)
+    rc = oracle().oracle_path_depth(steps.ctypes.data, steps.size, sp.ctypes.data, len(start), seg_len.ctypes.data,
+                                    seg_len.size, None if ids is None else ids.ctypes.data, n,
+                                    lengths.ctypes.data, means.ctypes.data)
+    return rc, lengths, means
+
+
+def format_float(x: float, digits: int = 2) -> str:
+    buf = C.create_string_buffer(600)
+    n = oracle().oracle_format_float(x, digits, buf, 600)
+    assert n >= 0
+    return buf.value.decode()
+
+
+def emit_path_depth(path_names, lengths, means) -> bytes:
+    """depth.rs:146-158 with the oracle's format_float."""
+    out = ["#path\tstart\tend\tmean.depth"]
+    for name, ln, m in zip(path_names, lengths, means):
+        out.append(f"{name}\t0\t{int(ln)}\t{format_float(float(m))}")
+    return ("\n".join(out) + "\n").encode()
 
 
 def file_depth(image: bytes):
