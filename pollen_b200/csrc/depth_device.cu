@@ -40,10 +40,11 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 constexpr size_t kDefaultBitmapBudget = 64ull << 20;  // stays resident in the 126 MB L2
-// Register cap / grid multiple for kernel A.  Shared memory (2 x 16 KiB per CTA) limits
-// residency to 6 CTAs per SM; a grid of 8 CTAs per SM measured best on B200 (the extra
-// CTAs start as the first ones drain, which evens out the tail).
-constexpr int kBlocksPerSM = 8;
+// Register cap / grid multiple for kernel A.  Shared memory (2 x 16 KiB staging + 8 KiB of
+// parked runs per CTA) limits residency to 5 CTAs per SM; a grid of twice that measured best
+// on B200 (the extra CTAs start as the first ones drain, which evens out the tail).
+constexpr int kBlocksPerSM = 5;
+constexpr int kGridPerSM = 10;
 
 }  // namespace
 
@@ -115,14 +116,17 @@ int launch_stream(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     P.depth = d_depth;
     P.bitmap = with_seen ? pl->d_bitmap + (size_t)(lo % pl->rows_per_batch) * pl->words_per_row : nullptr;
     P.err = pl->d_err;
-    const uint32_t grid = std::min<uint32_t>(chunks, (uint32_t)pl->sms * kBlocksPerSM);
+    const uint32_t grid = std::min<uint32_t>(chunks, (uint32_t)pl->sms * kGridPerSM);
     if (pl->probe_before) CU(cudaEventRecord(pl->probe_before, st));
     if (with_seen && pl->seen_mode == fgfa::kSeenWindow)
         fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenWindow>
             <<<grid, fgfa::kThreads, fgfa::stream_smem_bytes(fgfa::kSeenWindow), st>>>(P);
-    else if (with_seen)
+    else if (with_seen && pl->seen_mode == fgfa::kSeenDirect)
         fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenDirect>
             <<<grid, fgfa::kThreads, fgfa::stream_smem_bytes(fgfa::kSeenDirect), st>>>(P);
+    else if (with_seen)
+        fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenDeferred>
+            <<<grid, fgfa::kThreads, fgfa::stream_smem_bytes(fgfa::kSeenDeferred), st>>>(P);
     else
         fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenNone>
             <<<grid, fgfa::kThreads, fgfa::stream_smem_bytes(fgfa::kSeenNone), st>>>(P);
@@ -239,18 +243,21 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
     cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenWindow>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::stream_smem_bytes(fgfa::kSeenWindow));
     cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenDirect>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenDeferred>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenNone>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    // Seen-bit strategy.  Paths that are much longer than the graph has segments must loop
-    // (config E: tandem repeats), so their chunks keep hitting the same bitmap sectors and
-    // the shared-memory window pays off (measured 1.30 -> 1.09 ms on E); for haplotype-like
-    // paths the direct form is faster (0.73 vs 0.95 ms on C).  FGFA_SEEN_MODE overrides.
+    // Seen-bit strategy.  Default: parked runs issued by ordinal (kSeenDeferred; 0.66 ms on C
+    // against 0.72 for the direct form).  Paths that are much longer than the graph has
+    // segments must loop (config E: tandem repeats), so their chunks keep hitting the same
+    // bitmap sectors and the shared-memory window pays off (1.30 -> 1.09 ms on E, but 0.95 ms
+    // on C).  FGFA_SEEN_MODE=direct|deferred|window overrides.
     {
         uint64_t longest = 0;
         for (uint32_t p = 0; p < n_paths; ++p) longest = std::max<uint64_t>(longest, (uint64_t)h_span_end[p] - h_span_start[p]);
-        pl->seen_mode = (longest > 4ull * std::max<uint32_t>(n_segs, 1u)) ? fgfa::kSeenWindow : fgfa::kSeenDirect;
+        pl->seen_mode = (longest > 4ull * std::max<uint32_t>(n_segs, 1u)) ? fgfa::kSeenWindow : fgfa::kSeenDeferred;
         if (const char* env = std::getenv("FGFA_SEEN_MODE")) {
             if (!std::strcmp(env, "window")) pl->seen_mode = fgfa::kSeenWindow;
             else if (!std::strcmp(env, "direct")) pl->seen_mode = fgfa::kSeenDirect;
+            else if (!std::strcmp(env, "deferred")) pl->seen_mode = fgfa::kSeenDeferred;
         }
     }
     int rc = build_tables(pl, 0);

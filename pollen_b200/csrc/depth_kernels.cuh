@@ -127,20 +127,28 @@ constexpr uint32_t kFiller = 0xFFFFFFFFu;   // never a valid handle: segment ids
 // How kernel A records the seen-bits:
 //   kSeenNone    seg_depth only (depth.rs:45-56), no bitmap;
 //   kSeenDirect  one RED.OR per thread-level run, straight to L2;
+//   kSeenDeferred like kSeenDirect, but a thread parks its runs in a private shared-memory
+//                stack and the warp issues everybody's k-th run in the SAME instruction:
+//                neighbouring threads' k-th runs fall into the same 32-byte bitmap sector
+//                (a sector covers 256 segments, a thread ~19), so the L2 sees one request
+//                per sector instead of one per run.  No barrier, no atomics on shared memory.
 //   kSeenWindow  thread-level runs are first OR-ed into a block-wide shared-memory window
 //                (direct-mapped by bitmap-word index, one tag per 32-byte bitmap sector),
 //                then every touched sector is flushed with ONE coalesced RED.OR request.
 //                A chunk re-visits the same bitmap sectors many times (a sector covers 256
 //                segments), so this cuts the L2 reduction sectors of the seen-bits ~3-4x.
-enum SeenMode : int { kSeenNone = 0, kSeenDirect = 1, kSeenWindow = 2 };
+enum SeenMode : int { kSeenNone = 0, kSeenDirect = 1, kSeenWindow = 2, kSeenDeferred = 3 };
 
 constexpr uint32_t kWinWords = 4096;              // window: 4096 bitmap words = 131072 segments
 constexpr uint32_t kWinGroups = kWinWords / 8;    // one tag per bitmap sector (8 words)
 constexpr uint32_t kTagEmpty = 0xFFFFFFFFu;
 
+constexpr int kRunSlots = 4;                      // kSeenDeferred: parked runs per thread per chunk
+
 __host__ __device__ constexpr size_t stream_smem_bytes(int seen_mode) {
     return 2 * (size_t)kChunk * 4 +
-           (seen_mode == kSeenWindow ? (size_t)kWinWords * 4 + kWinGroups * 4 + kWinGroups * 4 + 16 : 0);
+           (seen_mode == kSeenWindow ? (size_t)kWinWords * 4 + kWinGroups * 4 + kWinGroups * 4 + 16 : 0) +
+           (seen_mode == kSeenDeferred ? (size_t)kRunSlots * kThreads * 8 : 0);
 }
 
 __device__ __forceinline__ void red_shared_or(uint32_t* p, uint32_t v) {
@@ -157,6 +165,7 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
     uint32_t* const s_tag = s_bits + kWinWords;                                          // [kWinGroups]
     uint32_t* const s_list = s_tag + kWinGroups;                                         // [kWinGroups]
     uint32_t* const s_count = s_list + kWinGroups;
+    uint2* const s_runs = reinterpret_cast<uint2*>(smem_dyn + 2 * (kChunk / 4)) + threadIdx.x;   // [kRunSlots][kThreads]
     if (SEEN_MODE == kSeenWindow) {
         for (uint32_t i = threadIdx.x; i < kWinWords; i += kThreads) s_bits[i] = 0u;
         for (uint32_t i = threadIdx.x; i < kWinGroups; i += kThreads) s_tag[i] = kTagEmpty;
@@ -224,14 +233,18 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
 #pragma unroll
             for (int i = 0; i < kItems; ++i) hmax = max(hmax, h[i]);
             if (hmax < seg_limit) {
-                uint32_t acc = 0;
+                uint32_t acc = 0, cnt = 0;
 #pragma unroll
                 for (int i = 0; i < kItems; ++i) {
                     const uint32_t bit = bit_of(h[i] >> 1);
                     acc = ((i > 0 && ((h[i] ^ h[i - 1]) < 64u)) ? acc : 0u) | bit;
                     if (i == kItems - 1 || ((h[i] ^ h[i + (i < kItems - 1)]) >= 64u)) {
                         const uint32_t w = h[i] >> 6;
-                        if (SEEN_MODE == kSeenWindow) {
+                        if (SEEN_MODE == kSeenDeferred) {
+                            if (cnt < kRunSlots) s_runs[cnt * kThreads] = make_uint2(w, acc);
+                            else red_or_b32(row + w, acc);
+                            ++cnt;
+                        } else if (SEEN_MODE == kSeenWindow) {
                             const uint32_t g = (w >> 3) & (kWinGroups - 1), tag = w >> 12;
                             uint32_t t = s_tag[g];
                             if (t == kTagEmpty) {
@@ -245,6 +258,15 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
                             else red_or_b32(row + w, acc);       // window slot taken by another sector
                         } else {
                             red_or_b32(row + w, acc);
+                        }
+                    }
+                }
+                if (SEEN_MODE == kSeenDeferred) {
+#pragma unroll
+                    for (int k = 0; k < kRunSlots; ++k) {
+                        if ((uint32_t)k < cnt) {
+                            const uint2 r = s_runs[k * kThreads];
+                            red_or_b32(row + r.x, r.y);
                         }
                     }
                 }

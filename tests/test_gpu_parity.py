@@ -222,11 +222,11 @@ def test_plan_reuse_batches_and_feed_pipeline(torch_cuda):
         plan.close()
 
 
-@pytest.mark.parametrize("mode", ["direct", "window"])
+@pytest.mark.parametrize("mode", ["direct", "deferred", "window"])
 def test_both_seen_bit_strategies(torch_cuda, mode, monkeypatch):
-    """Kernel A's two ways of recording seen-bits (straight RED.OR per run / shared-memory
-    window flushed per bitmap sector) give identical results; the plan picks one by path
-    length, FGFA_SEEN_MODE forces it."""
+    """Kernel A's ways of recording seen-bits (straight RED.OR per run / runs parked and
+    issued by ordinal / shared-memory window flushed per bitmap sector) give identical
+    results; the plan picks one by path length, FGFA_SEEN_MODE forces it."""
     torch = torch_cuda
     monkeypatch.setenv("FGFA_SEEN_MODE", mode)
     for name in ("tiny", "tinyE", "B"):

@@ -215,6 +215,13 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(k_step_stream_merged<4, kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smW));
         time_it("merged direct-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenDirect><<<sms * 4, kThreads, smD>>>(S); }, true);
         time_it("merged direct-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenDirect><<<sms * 8, kThreads, smD>>>(S); }, true);
+        const size_t smF = stream_smem_bytes(kSeenDeferred);
+        time_it("merged deferred-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenDeferred><<<sms * 4, kThreads, smF>>>(S); }, true);
+        time_it("merged deferred-OR <4> grid 8x", [&] { k_step_stream_merged<4, kSeenDeferred><<<sms * 8, kThreads, smF>>>(S); }, true);
+        time_it("merged deferred-OR <5> grid 5x", [&] { k_step_stream_merged<5, kSeenDeferred><<<sms * 5, kThreads, smF>>>(S); }, true);
+        time_it("merged deferred-OR <5> grid 10x", [&] { k_step_stream_merged<5, kSeenDeferred><<<sms * 10, kThreads, smF>>>(S); }, true);
+        time_it("merged deferred-OR <6> grid 5x", [&] { k_step_stream_merged<6, kSeenDeferred><<<sms * 5, kThreads, smF>>>(S); }, true);
+        time_it("merged deferred-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenDeferred><<<sms * 8, kThreads, smF>>>(S); }, true);
         time_it("merged window-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenWindow><<<sms * 4, kThreads, smW>>>(S); }, true);
         time_it("merged window-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenWindow><<<sms * 8, kThreads, smW>>>(S); }, true);
         time_it("merged depth-only g=8xSM", [&] { k_step_stream_merged<8, kSeenNone><<<sms * 8, kThreads, smD>>>(S); }, true);
@@ -232,7 +239,7 @@ int main(int argc, char** argv) {
             for (int r = 0; r < reps + 2; ++r) {
                 CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
-                if (use_merged) k_step_stream_merged<8, kSeenWindow><<<sms * 8, kThreads, stream_smem_bytes(kSeenWindow)>>>(S); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
+                if (use_merged) k_step_stream_merged<8, kSeenDeferred><<<sms * 8, kThreads, stream_smem_bytes(kSeenDeferred)>>>(S); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
                 k_uniq_popcount<<<pgrid, kPopThreads>>>(Q2);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
