@@ -156,9 +156,13 @@ __device__ __forceinline__ void red_shared_or(uint32_t* p, uint32_t v) {
     asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-template <int BLOCKS_PER_SM, int SEEN_MODE>
+// P2 = consecutive steps one thread walks per pass-2 round (kItems/P2 rounds per chunk).
+// Smaller P2 packs the lanes of one RED.OR instruction closer together in segment space
+// (fewer bitmap sectors per instruction) at the price of shorter runs.
+template <int BLOCKS_PER_SM, int SEEN_MODE, int P2 = kItems>
 __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(StreamParams P) {
     constexpr bool WITH_SEEN = SEEN_MODE != kSeenNone;
+    static_assert(P2 == 16 || P2 == 8 || P2 == 4, "P2 must divide kItems and be a multiple of 4");
     extern __shared__ uint4 smem_dyn[];
     uint4 (*s_steps)[kChunk / 4] = reinterpret_cast<uint4 (*)[kChunk / 4]>(smem_dyn);
     uint32_t* const s_bits = reinterpret_cast<uint32_t*>(smem_dyn + 2 * (kChunk / 4));   // [kWinWords]
@@ -175,8 +179,9 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t seg_limit = P.n_segs * 2u;   // h < seg_limit  <=>  (h >> 1) < n_segs  (n_segs < 2^31)
     const uint32_t st_off = swz(tid);                               // staging: vector tid + j*kThreads
-    const uint32_t swc = (tid >> 1) & 7u;                           // pass 2: vectors 4*tid + j
-    const uint32_t ld_base = (tid * 4u) & ~7u, ld_lo = 4u * (tid & 1u);
+    constexpr uint32_t kVecs = P2 / 4;                              // pass 2: vectors kVecs*tid + j (+ round)
+    const uint32_t swc = ((tid * kVecs) >> 3) & 7u;
+    const uint32_t ld_base = (tid * kVecs) & ~7u, ld_lo = (tid * kVecs) & 7u;
     // pass 3: element i*kThreads + tid lives in vector i*64 + warp*8 + lane/4
     const uint32_t p3_off = (warp * 8u + ((lane >> 2) ^ (warp & 7u))) * 4u + (lane & 3u);
     uint32_t* const depth_ptr = keep_ptr(P.depth);
@@ -223,22 +228,25 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
         // ---- pass 2: thread order -- one RED.OR per run of steps in the same bitmap word ----
         if (WITH_SEEN) {
             uint32_t* __restrict__ row = P.bitmap + (size_t)(cur.path - P.path_lo) * P.words_per_row;
-            uint32_t h[kItems];
 #pragma unroll
-            for (int j = 0; j < kItems / 4; ++j) {
-                const uint4 x = buf[ld_base + ((ld_lo + j) ^ swc)];
+            for (int round = 0; round < kItems / P2; ++round) {
+            uint32_t h[P2];
+#pragma unroll
+            for (int j = 0; j < P2 / 4; ++j) {
+                const uint4 x = buf[round * (kThreads * kVecs) + ld_base + ((ld_lo + j) ^ swc)];
                 h[4 * j + 0] = x.x; h[4 * j + 1] = x.y; h[4 * j + 2] = x.z; h[4 * j + 3] = x.w;
             }
             uint32_t hmax = 0;
 #pragma unroll
-            for (int i = 0; i < kItems; ++i) hmax = max(hmax, h[i]);
+            for (int i = 0; i < P2; ++i) hmax = max(hmax, h[i]);
+            uint32_t cnt_out = 0;                 // runs parked by this thread (kSeenDeferred)
             if (hmax < seg_limit) {
                 uint32_t acc = 0, cnt = 0;
 #pragma unroll
-                for (int i = 0; i < kItems; ++i) {
+                for (int i = 0; i < P2; ++i) {
                     const uint32_t bit = bit_of(h[i] >> 1);
                     acc = ((i > 0 && ((h[i] ^ h[i - 1]) < 64u)) ? acc : 0u) | bit;
-                    if (i == kItems - 1 || ((h[i] ^ h[i + (i < kItems - 1)]) >= 64u)) {
+                    if (i == P2 - 1 || ((h[i] ^ h[i + (i < P2 - 1)]) >= 64u)) {
                         const uint32_t w = h[i] >> 6;
                         if (SEEN_MODE == kSeenDeferred) {
                             if (cnt < kRunSlots) s_runs[cnt * kThreads] = make_uint2(w, acc);
@@ -261,23 +269,27 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
                         }
                     }
                 }
-                if (SEEN_MODE == kSeenDeferred) {
-#pragma unroll
-                    for (int k = 0; k < kRunSlots; ++k) {
-                        if ((uint32_t)k < cnt) {
-                            const uint2 r = s_runs[k * kThreads];
-                            red_or_b32(row + r.x, r.y);
-                        }
-                    }
-                }
+                cnt_out = cnt;
             } else {
                 // filler (edge chunk) or out-of-range segment id somewhere: per step, unmerged
 #pragma unroll
-                for (int i = 0; i < kItems; ++i) {
+                for (int i = 0; i < P2; ++i) {
                     if (h[i] < seg_limit) red_or_b32(row + (h[i] >> 6), bit_of(h[i] >> 1));
                     else if (h[i] != kFiller) *P.err = 1u;
                 }
             }
+            // issue the parked runs by ordinal: everybody's k-th run in the same instruction
+            if (SEEN_MODE == kSeenDeferred) {
+                const uint32_t cnt = cnt_out;
+#pragma unroll
+                for (int k = 0; k < kRunSlots; ++k) {
+                    if ((uint32_t)k < cnt) {
+                        const uint2 r = s_runs[k * kThreads];
+                        red_or_b32(row + r.x, r.y);
+                    }
+                }
+            }
+            }   // round
         }
         // ---- pass 3: lane order -- one depth RED.ADD per step ----
         {

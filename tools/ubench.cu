@@ -219,6 +219,10 @@ int main(int argc, char** argv) {
         time_it("merged deferred-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenDeferred><<<sms * 4, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR <4> grid 8x", [&] { k_step_stream_merged<4, kSeenDeferred><<<sms * 8, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR <5> grid 5x", [&] { k_step_stream_merged<5, kSeenDeferred><<<sms * 5, kThreads, smF>>>(S); }, true);
+        time_it("deferred-OR P2=8 <5> grid 10x", [&] { k_step_stream_merged<5, kSeenDeferred, 8><<<sms * 10, kThreads, smF>>>(S); }, true);
+        time_it("deferred-OR P2=8 <4> grid 8x", [&] { k_step_stream_merged<4, kSeenDeferred, 8><<<sms * 8, kThreads, smF>>>(S); }, true);
+        time_it("deferred-OR P2=8 <6> grid 10x", [&] { k_step_stream_merged<6, kSeenDeferred, 8><<<sms * 10, kThreads, smF>>>(S); }, true);
+        time_it("deferred-OR P2=4 <5> grid 10x", [&] { k_step_stream_merged<5, kSeenDeferred, 4><<<sms * 10, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR <5> grid 10x", [&] { k_step_stream_merged<5, kSeenDeferred><<<sms * 10, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR <6> grid 5x", [&] { k_step_stream_merged<6, kSeenDeferred><<<sms * 5, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenDeferred><<<sms * 8, kThreads, smF>>>(S); }, true);
@@ -239,7 +243,7 @@ int main(int argc, char** argv) {
             for (int r = 0; r < reps + 2; ++r) {
                 CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
-                if (use_merged) k_step_stream_merged<8, kSeenDeferred><<<sms * 8, kThreads, stream_smem_bytes(kSeenDeferred)>>>(S); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
+                if (use_merged) k_step_stream_merged<5, kSeenDeferred><<<sms * 10, kThreads, stream_smem_bytes(kSeenDeferred)>>>(S); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
                 k_uniq_popcount<<<pgrid, kPopThreads>>>(Q2);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
