@@ -128,8 +128,9 @@ def run_reference(args, cfg, rank):
     }))
 
 
-def workload_config(cfg, n_gpus):
+def workload_config(cfg, n_gpus, exchange=None):
     return {
+        **({"exchange": exchange} if exchange else {}),
         "workload": f"{cfg.name}: {cfg.description}",
         "n_segs": cfg.n_segs, "n_paths": cfg.n_paths, "n_steps": cfg.n_steps,
         "generator": "haplotype walk (SURVEY.md 8d), seed 0xB1011054" if cfg.kind == 0 else "see pollen_b200/csrc/synth.cpp",
@@ -184,8 +185,45 @@ def main():
     d_steps = torch.empty(n_local, dtype=torch.int32, device=dev)
     d_steps.copy_(h_steps)
     eng = sharding.ShardedDepth(ls, le, cfg.n_segs, dev, n_paths_global=cfg.n_paths if world > 1 else None)
+    exchange = "none (single GPU)" if world == 1 else "nccl all_reduce of [depth u32 | uniq u8]" if eng.compact else "nccl all_reduce of [depth u32 | uniq u32]"
+    if world > 1 and cfg.n_paths <= 255 and os.environ.get("FGFA_EXCHANGE", "fused") == "fused":
+        # Preferred exchange: popcount fused with a reduce-scatter/all-gather over NVLink peer
+        # memory (kernel X).  It is checked against the NCCL engine once, here, and dropped if
+        # symmetric memory is unavailable on this box or the results differ.
+        try:
+            fused = sharding.FusedShardedDepth(ls, le, cfg.n_segs, dev, [len(p) for p in parts])
+            st0 = torch.cuda.current_stream(dev)
+            eng.run(d_steps, st0)
+            fused.run(d_steps, st0)
+            torch.cuda.synchronize(dev)
+            same = torch.equal(eng.depth, fused.depth) and torch.equal(eng.uniq, fused.uniq)
+
+            def probe(e, reps=8):
+                for _ in range(3):
+                    e.run(d_steps, st0)
+                torch.cuda.synchronize(dev)
+                dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st0)
+                for _ in range(reps):
+                    e.run(d_steps, st0)
+                b.record(st0)
+                torch.cuda.synchronize(dev)
+                return a.elapsed_time(b) / reps
+            t = torch.tensor([probe(eng), probe(fused), 0.0 if same else 1.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_nccl, t_fused, bad = (float(x) for x in t.tolist())
+            if bad == 0.0 and t_fused < t_nccl:        # every rank takes the same decision
+                eng = fused
+                exchange = "fused popcount + reduce-scatter/all-gather over NVLink peer memory (kernel X%s); probe: %.3f ms vs %.3f ms with nccl" % (
+                    ", multicast stores" if fused.mc_ptr else "", t_fused, t_nccl)
+            else:
+                exchange += "; probe: %.3f ms vs %.3f ms with the fused exchange%s" % (t_nccl, t_fused, "" if bad == 0.0 else " (MISMATCH)")
+                del fused
+        except Exception as exc:  # symmetric memory not available: keep NCCL
+            exchange += f" (fused exchange unavailable: {type(exc).__name__})"
     stream = torch.cuda.current_stream(dev)
-    launches_per_step = eng.plan.launches(True)
+    launches_per_step = eng.plan.launches(True) if isinstance(eng, sharding.ShardedDepth) else 2   # kernel A + B, or A + X
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -260,12 +298,18 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-    depth_only_ms = timed(lambda: eng.plan.run(d_steps, eng.depth, None, stream.cuda_stream), args.steps)
-    allreduce_ms = timed(lambda: sharding.allreduce_counts(eng.out), args.steps) if world > 1 else 0.0
+    scratch_depth = torch.empty(cfg.n_segs, dtype=torch.int32, device=dev)
+    depth_only_ms = timed(lambda: eng.plan.run(d_steps, scratch_depth, None, stream.cuda_stream), args.steps)
+    if world > 1 and isinstance(eng, sharding.ShardedDepth):
+        allreduce_ms = timed(lambda: sharding.allreduce_counts(eng.out), args.steps)
+    elif world > 1:
+        allreduce_ms = max(0.0, ms_per_step - k_ms)      # barriers + kernel X + bitmap reset
+    else:
+        allreduce_ms = 0.0
     eng.run(d_steps, stream)          # leave a valid result behind
     eng.status()
     split = {"depth_only_ms_per_step": depth_only_ms, "depth_only_steps_per_s": cfg.n_steps / (depth_only_ms * 1e-3),
-             "allreduce_ms": allreduce_ms, "allreduce_bytes": eng.exchange_bytes if world > 1 else 0,
+             "exchange_ms": allreduce_ms, "exchange_bytes_per_rank": eng.exchange_bytes if world > 1 else 0,
              "stream_kernel_ms": k_ms}
 
     # ---- end to end: host buffers in, host results out ---------------------------------
@@ -291,13 +335,15 @@ def main():
         assert int(d64.sum()) == cfg.n_steps
         e2e_api = "fgfa_seg_depth_with_uniq_steps (C ABI, pinned host steps)"
     else:
-        out_host = torch.empty(eng.out.numel(), dtype=torch.int32).pin_memory()
+        res_dev = (eng.out,) if isinstance(eng, sharding.ShardedDepth) else (eng.depth, eng.uniq)
+        res_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res_dev]
 
         def e2e_once():
             d_steps.copy_(h_steps, non_blocking=True)
             eng.run(d_steps, stream)
             if rank == 0:                      # the table is printed by one process
-                out_host.copy_(eng.out, non_blocking=True)
+                for h, t in zip(res_host, res_dev):
+                    h.copy_(t, non_blocking=True)
             stream.synchronize()
         e2e_once()
         barrier()
@@ -308,9 +354,9 @@ def main():
         e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         e2e_s = float(e2e_t.item())
-        e2e_api = "ShardedDepth.run on pinned host shards (H2D + kernels + NCCL allreduce + D2H)"
+        e2e_api = "%s.run on pinned host shards (H2D + kernels + exchange + D2H on rank 0)" % type(eng).__name__
     e2e = {"value": cfg.n_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local + 8 * len(my_paths),
-           "d2h_bytes_per_step": eng.exchange_bytes if world > 1 else 8 * cfg.n_segs, "ms_per_step": e2e_s * 1e3, "api": e2e_api, "steps": e2e_steps}
+           "d2h_bytes_per_step": 5 * cfg.n_segs if (world > 1 and eng.compact) else 8 * cfg.n_segs, "ms_per_step": e2e_s * 1e3, "api": e2e_api, "steps": e2e_steps}
 
     clocks = sampler.stop() if sampler else None
 
@@ -327,7 +373,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload_config(cfg, world), "roofline": roofline, "split": split, "cpu_baseline": cpu, "e2e": e2e,
+            "config": workload_config(cfg, world, exchange), "roofline": roofline, "split": split, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }))
     if world > 1:

@@ -87,6 +87,29 @@ int fgfa_depth_plan_finish(fgfa_depth_plan_t* plan, uint32_t* d_uniq, void* cuda
  * last call: FGFA_OK, FGFA_ERR_SEG_OOB or FGFA_ERR_CUDA. */
 int fgfa_depth_plan_status(fgfa_depth_plan_t* plan, void* cuda_stream);
 
+/* ---- fused popcount + exchange over NVLink peer memory (multi-GPU) ------------------
+ * The plan's seen-bitmap can live in caller-provided (symmetric, peer-mapped) memory:
+ * `bytes` >= words_per_row*4*n_paths with words_per_row = ceil(n_segs/32) rounded up to 32,
+ * 128-byte aligned, zero on first use; the caller re-zeroes it after every exchange. */
+int fgfa_depth_plan_use_bitmap(fgfa_depth_plan_t* plan, void* d_bitmap, size_t bytes);
+/* Zero d_depth and run only the step-stream kernel: partial depth + seen-bits, no popcount. */
+int fgfa_depth_plan_run_stream_only(fgfa_depth_plan_t* plan, const uint32_t* d_steps, uint32_t* d_depth,
+                                    void* cuda_stream);
+/* One launch on rank `rank`: for this rank's slice of the segment axis, sum all ranks'
+ * partial depths, popcount all ranks' bitmap rows (rows[q] rows of pitch words_per_row at
+ * bitmaps[q]) and store final depth (u32) / uniq (u8) into every rank's result buffers.
+ * All pointers are device pointers valid in THIS process (peer mappings).  The caller
+ * orders the launch between two inter-rank barriers on the same stream.  <= 255 paths.
+ * multicast_base (optional, else NULL): NVLS multicast mapping of a symmetric buffer that
+ * holds partial depth / final depth / final uniq at the given byte offsets on every rank;
+ * with it the depth sum is an in-switch `multimem.ld_reduce` and the all-gather a
+ * `multimem.st`, so a rank moves one slice in and one slice out instead of N-1 of each. */
+int fgfa_exchange_uniq_depth(int n_ranks, int rank, const void* const* bitmaps, const uint32_t* rows,
+                             const void* const* partial_depths, void* const* final_depths,
+                             void* const* final_uniqs, uint32_t n_segs, void* multicast_base,
+                             uint64_t off_partial, uint64_t off_final_depth, uint64_t off_final_uniq,
+                             void* cuda_stream);
+
 /* Width of the uniq counters the plan's runs write to d_uniq: 4 (default, u32) or 1 (u8;
  * only for plans of <= 255 paths, since uniq <= n_paths).  The narrow form exists for the
  * multi-GPU exchange: [depth u32 | uniq u8] is 25 MB instead of 40 MB at 5 M segments, and

@@ -75,6 +75,9 @@ EXPORTS = {
     "fgfa_depth_plan_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fgfa_depth_plan_use_bitmap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fgfa_depth_plan_run_stream_only": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_exchange_uniq_depth": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "fgfa_depth_plan_set_uniq_width": (C.c_int, [C.c_void_p, C.c_int]),
     "fgfa_depth_plan_set_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_launches": (C.c_uint32, [C.c_void_p, C.c_int]),
@@ -287,6 +290,16 @@ class SegDepth:
         return self.gfa.format_seg_depth(self.depths, self.uniq_depths)
 
 
+def exchange_uniq_depth(n_ranks, rank, bitmaps, rows, partial_depths, final_depths, final_uniqs, n_segs, stream=0,
+                        multicast_base=0, off_partial=0, off_final_depth=0, off_final_uniq=0):
+    """One fused popcount + exchange launch (see fgfa_exchange_uniq_depth)."""
+    P = C.c_void_p * n_ranks
+    r = np.ascontiguousarray(rows, dtype=np.uint32)
+    _check(lib().fgfa_exchange_uniq_depth(n_ranks, rank, P(*bitmaps), r.ctypes.data, P(*partial_depths),
+                                          P(*final_depths), P(*final_uniqs), n_segs, multicast_base or None,
+                                          off_partial, off_final_depth, off_final_uniq, stream or None))
+
+
 class DepthPlan:
     """Device-resident form: a plan (chunk table + seen-bitmap scratch) run on device
     buffers.  Buffers are torch CUDA tensors (uint32 viewed as int32 is fine: only
@@ -335,6 +348,18 @@ class DepthPlan:
     def status(self, stream: int = 0) -> None:
         """Synchronise and raise DepthError if a run saw an out-of-range segment id."""
         _check(lib().fgfa_depth_plan_status(self._h, stream or None))
+
+    def use_bitmap(self, ptr: int, nbytes: int) -> None:
+        """Keep the seen-bitmap in caller-provided (peer-mapped) device memory."""
+        _check(lib().fgfa_depth_plan_use_bitmap(self._h, ptr, nbytes))
+
+    def run_stream_only(self, d_steps, depth_ptr: int, stream: int = 0) -> None:
+        """memset(depth) + kernel A only (partial depth + seen-bits); no popcount."""
+        _check(lib().fgfa_depth_plan_run_stream_only(self._h, self._ptr(d_steps), depth_ptr, stream or None))
+
+    @property
+    def bitmap_row_bytes(self) -> int:
+        return ((((self.n_segs + 31) // 32) + 31) // 32 * 32) * 4
 
     def set_uniq_width(self, nbytes: int) -> None:
         """uniq counters as u32 (4, default) or u8 (1; plans of <= 255 paths)."""

@@ -59,6 +59,7 @@ struct fgfa_depth_plan {
     size_t chunk_capacity = 0;
     std::vector<uint32_t> h_prefix;        // chunks before path p, [n_paths+1]
     uint32_t* d_bitmap = nullptr;          // [rows_per_batch][words_per_row], zero between runs
+    bool own_bitmap = true;                // false: caller-provided (symmetric) memory
     uint32_t* d_err = nullptr;
     size_t scratch_bytes = 0;
     int uniq_bytes = 4;                    // width of the uniq counters kernel B writes
@@ -270,7 +271,7 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
 void fgfa_depth_plan_destroy(fgfa_depth_plan_t* pl) {
     if (!pl) return;
     cudaFree(pl->d_chunks);
-    cudaFree(pl->d_bitmap);
+    if (pl->own_bitmap) cudaFree(pl->d_bitmap);
     cudaFree(pl->d_err);
     delete pl;
 }
@@ -342,6 +343,79 @@ int fgfa_depth_plan_status(fgfa_depth_plan_t* pl, void* cuda_stream) {
         CU(cudaMemsetAsync(pl->d_err, 0, 4, st));
         CU(cudaStreamSynchronize(st));
         return fail(FGFA_ERR_SEG_OOB, "a step refers to a segment index >= n_segs");
+    }
+    return FGFA_OK;
+}
+
+int fgfa_depth_plan_use_bitmap(fgfa_depth_plan_t* pl, void* d_bitmap, size_t bytes) {
+    if (!pl || !d_bitmap) return fail(FGFA_ERR_INVALID_ARG, "null argument");
+    const size_t need = (size_t)pl->words_per_row * 4 * std::max<uint32_t>(pl->n_paths, 1u);
+    if (bytes < need || ((uintptr_t)d_bitmap & 127u))
+        return fail(FGFA_ERR_INVALID_ARG, "external bitmap must be 128-byte aligned and hold one row per path");
+    if (pl->own_bitmap) cudaFree(pl->d_bitmap);
+    pl->d_bitmap = static_cast<uint32_t*>(d_bitmap);
+    pl->own_bitmap = false;
+    pl->rows_per_batch = std::max<uint32_t>(pl->n_paths, 1u);   // one batch: every path has its row
+    return FGFA_OK;
+}
+
+int fgfa_depth_plan_run_stream_only(fgfa_depth_plan_t* pl, const uint32_t* d_steps, uint32_t* d_depth,
+                                    void* cuda_stream) {
+    if (!pl || (!d_depth && pl->n_segs)) return fail(FGFA_ERR_INVALID_ARG, "null argument");
+    if (pl->rows_per_batch < pl->n_paths) return fail(FGFA_ERR_INVALID_ARG, "the bitmap must hold every path (one batch)");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (pl->n_segs) CU(cudaMemsetAsync(d_depth, 0, (size_t)pl->n_segs * 4, st));
+    if (pl->n_paths == 0 || pl->n_steps == 0) return FGFA_OK;
+    const uint32_t* base = d_steps;
+    int rc = prepare_pointer(pl, d_steps, &base);
+    if (rc) return rc;
+    return launch_stream(pl, base, 0, pl->n_paths, d_depth, true, st);
+}
+
+int fgfa_exchange_uniq_depth(int n_ranks, int rank, const void* const* bitmaps, const uint32_t* rows,
+                             const void* const* partial_depths, void* const* final_depths,
+                             void* const* final_uniqs, uint32_t n_segs, void* multicast_base,
+                             uint64_t off_partial, uint64_t off_final_depth, uint64_t off_final_uniq,
+                             void* cuda_stream) {
+    if (n_ranks < 1 || n_ranks > fgfa::kMaxRanks || rank < 0 || rank >= n_ranks || !bitmaps || !rows ||
+        !partial_depths || !final_depths || !final_uniqs)
+        return fail(FGFA_ERR_INVALID_ARG, "bad exchange arguments");
+    uint64_t total_rows = 0;
+    for (int q = 0; q < n_ranks; ++q) total_rows += rows[q];
+    if (total_rows > 255) return fail(FGFA_ERR_INVALID_ARG, "the fused exchange carries u8 uniq counters (<= 255 paths)");
+    const uint32_t n_words = (n_segs + 31) / 32;
+    const uint32_t words_per_row = (n_words + 31) & ~31u;
+    fgfa::ExchangeParams X{};
+    uint32_t k = 0;
+    for (int q = 0; q < n_ranks; ++q) {
+        for (uint32_t r = 0; r < rows[q]; ++r)
+            X.row_ptr[k++] = static_cast<const uint32_t*>(bitmaps[q]) + (size_t)r * words_per_row;
+        X.partial_depth[q] = static_cast<const uint32_t*>(partial_depths[q]);
+        X.final_depth[q] = static_cast<uint32_t*>(final_depths[q]);
+        X.final_uniq[q] = static_cast<uint8_t*>(final_uniqs[q]);
+    }
+    X.mc_base = static_cast<uint8_t*>(multicast_base);
+    X.off_partial = off_partial;
+    X.off_final_depth = off_final_depth;
+    X.off_final_uniq = off_final_uniq;
+    {   // FGFA_MC_REDUCE=1: in-switch depth sum (multimem.ld_reduce); default: peer loads + multicast stores
+        const char* env = std::getenv("FGFA_MC_REDUCE");
+        X.mc_reduce = (env && env[0] == '1') ? 1 : 0;
+    }
+    if (multicast_base && ((off_partial | off_final_depth | off_final_uniq) & 15u))
+        return fail(FGFA_ERR_INVALID_ARG, "multicast regions must be 16-byte aligned");
+    X.n_ranks = n_ranks;
+    X.n_rows = k;
+    X.n_segs = n_segs;
+    const uint32_t per = ((n_words + n_ranks - 1) / n_ranks + 31) & ~31u;   // slices of whole 128-byte lines
+    X.w_lo = (uint32_t)std::min<uint64_t>((uint64_t)per * rank, n_words);
+    X.w_hi = (uint32_t)std::min<uint64_t>((uint64_t)per * (rank + 1), n_words);
+    if (X.w_hi > X.w_lo) {
+        const uint32_t words = X.w_hi - X.w_lo;
+        X.uniq_blocks = (words + fgfa::kXThreads - 1) / fgfa::kXThreads;
+        const uint32_t depth_blocks = (words * 8 + fgfa::kXThreads - 1) / fgfa::kXThreads;   // 4 segments per thread
+        fgfa::k_uniq_exchange<<<X.uniq_blocks + depth_blocks, fgfa::kXThreads, 0, (cudaStream_t)cuda_stream>>>(X);
+        CU(cudaGetLastError());
     }
     return FGFA_OK;
 }

@@ -489,4 +489,149 @@ __global__ void __launch_bounds__(kThreads) k_path_measure(MeasureParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// kernel X (k_uniq_exchange): kernel B fused with the multi-GPU exchange, over NVLink peer
+// memory.  Every rank owns one slice of the segment axis.  For its slice it
+//   * sums the ranks' partial depths                       (the reduce-scatter of depth),
+//   * popcounts the seen-bitmap rows of ALL ranks          (uniq never needs reducing),
+//   * stores the final depth (u32) and uniq (u8) slice into EVERY rank's result buffer
+//     (the all-gather), with plain peer loads/stores on symmetric-memory pointers.
+// A rank moves (N-1)/N of [4 B depth + rows/8 B bitmap] per slice segment in and
+// (N-1) x 5 B per slice segment out, instead of NCCL's allreduce of the whole 5 B/segment
+// buffer; inter-rank ordering is two stream barriers around the launch (host side).
+// ---------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+constexpr int kMaxRows = 255;                   // u8 uniq counters: at most 255 paths in the graph
+
+struct ExchangeParams {
+    const uint32_t* row_ptr[kMaxRows];          // every rank's seen-bitmap rows, flattened (peer pointers)
+    const uint32_t* partial_depth[kMaxRanks];   // rank q's partial depth [n_segs]
+    uint32_t* final_depth[kMaxRanks];           // rank q's result depth [n_segs]
+    uint8_t* final_uniq[kMaxRanks];             // rank q's result uniq  [n_segs]
+    int n_ranks;
+    uint32_t n_rows;                            // total rows over all ranks
+    uint32_t n_segs;
+    uint32_t w_lo, w_hi;                        // this rank's slice of bitmap words (32 segments each)
+    uint32_t uniq_blocks;                       // blocks [0, uniq_blocks) popcount, the rest sum depths
+    // NVLS: multicast mapping of the symmetric buffer (nullptr = plain peer loads/stores) and
+    // the byte offsets of the three regions inside it (identical on every rank)
+    uint8_t* mc_base;
+    uint64_t off_partial, off_final_depth, off_final_uniq;
+    int mc_reduce;                              // 1: depth sum by multimem.ld_reduce, 0: by peer loads
+};
+
+// multimem.*: one instruction on the multicast address reaches every rank's copy through
+// the NVSwitch -- ld_reduce returns the in-switch SUM of all ranks' words, st stores to all.
+__device__ __forceinline__ uint64_t mc_ld_reduce_add_u64(const void* mc) {
+    uint64_t r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(r) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void mc_st_v4(void* mc, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+
+constexpr int kXThreads = 128;
+constexpr int kXRowsInFlight = 32;
+
+__device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_peer_u32(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+__global__ void __launch_bounds__(kXThreads) k_uniq_exchange(ExchangeParams P) {
+    if (blockIdx.x < P.uniq_blocks) {
+        // ---- role 1: uniq = bit-sliced count over every rank's rows of one column word ----
+        const uint32_t w = P.w_lo + blockIdx.x * kXThreads + threadIdx.x;
+        if (w >= P.w_hi) return;
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+        for (uint32_t r0 = 0; r0 < P.n_rows; r0 += kXRowsInFlight) {
+            uint32_t x[kXRowsInFlight];
+#pragma unroll
+            for (int k = 0; k < kXRowsInFlight; ++k)
+                x[k] = (r0 + k < P.n_rows) ? ld_peer_u32(P.row_ptr[r0 + k] + w) : 0u;
+#pragma unroll
+            for (int k = 0; k < kXRowsInFlight; ++k) {
+                uint32_t v = x[k], t;
+                t = c0 & v; c0 ^= v; v = t;
+                t = c1 & v; c1 ^= v; v = t;
+                t = c2 & v; c2 ^= v; v = t;
+                t = c3 & v; c3 ^= v; v = t;
+                t = c4 & v; c4 ^= v; v = t;
+                t = c5 & v; c5 ^= v; v = t;
+                t = c6 & v; c6 ^= v; v = t;
+                c7 ^= v;                        // <= 255 rows in total: eight planes never overflow
+            }
+        }
+        uint32_t packed[8];                     // 32 u8 counts, segment 32w + j in byte j
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t cnt = ((c0 >> j) & 1u) | (((c1 >> j) & 1u) << 1) | (((c2 >> j) & 1u) << 2) |
+                                 (((c3 >> j) & 1u) << 3) | (((c4 >> j) & 1u) << 4) | (((c5 >> j) & 1u) << 5) |
+                                 (((c6 >> j) & 1u) << 6) | (((c7 >> j) & 1u) << 7);
+            if ((j & 3) == 0) packed[j >> 2] = cnt; else packed[j >> 2] |= cnt << (8 * (j & 3));
+        }
+        const uint32_t seg0 = w << 5;
+        if (seg0 + 32u <= P.n_segs && P.mc_base) {     // all-gather through the switch
+            uint8_t* du = P.mc_base + P.off_final_uniq + seg0;
+            mc_st_v4(du, make_uint4(packed[0], packed[1], packed[2], packed[3]));
+            mc_st_v4(du + 16, make_uint4(packed[4], packed[5], packed[6], packed[7]));
+        } else if (seg0 + 32u <= P.n_segs) {
+            for (int q = 0; q < P.n_ranks; ++q) {      // all-gather by peer stores
+                uint4* du = reinterpret_cast<uint4*>(P.final_uniq[q] + seg0);
+                du[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                du[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+        } else {
+            for (uint32_t j = 0; seg0 + j < P.n_segs; ++j)
+                for (int q = 0; q < P.n_ranks; ++q)
+                    P.final_uniq[q][seg0 + j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
+        }
+    } else {
+        // ---- role 2: depth = sum of the ranks' partials, four segments per thread ----
+        const uint64_t s_lo = (uint64_t)P.w_lo << 5, s_hi = min((uint64_t)P.w_hi << 5, (uint64_t)P.n_segs);
+        const uint64_t seg = s_lo + ((uint64_t)(blockIdx.x - P.uniq_blocks) * kXThreads + threadIdx.x) * 4;
+        if (seg >= s_hi) return;
+        if (seg + 4 <= s_hi && P.mc_base && P.mc_reduce) {
+            // two packed-u32 sums per 64-bit in-switch reduction: a true depth never carries
+            // out of its 32 bits (depth <= n_steps < 2^32)
+            const uint8_t* src = P.mc_base + P.off_partial + seg * 4;
+            const uint64_t lo = mc_ld_reduce_add_u64(src), hi = mc_ld_reduce_add_u64(src + 8);
+            mc_st_v4(P.mc_base + P.off_final_depth + seg * 4,
+                     make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)));
+        } else if (seg + 4 <= s_hi) {
+            uint4 t[kMaxRanks];
+#pragma unroll
+            for (int q = 0; q < kMaxRanks; ++q)
+                if (q < P.n_ranks) t[q] = ld_peer_v4(reinterpret_cast<const uint4*>(P.partial_depth[q] + seg));
+            uint4 d = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int q = 0; q < kMaxRanks; ++q)
+                if (q < P.n_ranks) { d.x += t[q].x; d.y += t[q].y; d.z += t[q].z; d.w += t[q].w; }
+            if (P.mc_base) {
+                mc_st_v4(P.mc_base + P.off_final_depth + seg * 4, d);
+            } else {
+#pragma unroll
+                for (int q = 0; q < kMaxRanks; ++q)
+                    if (q < P.n_ranks) *reinterpret_cast<uint4*>(P.final_depth[q] + seg) = d;
+            }
+        } else {
+            for (uint64_t s2 = seg; s2 < s_hi; ++s2) {
+                uint32_t sum = 0;
+                for (int q = 0; q < P.n_ranks; ++q) sum += ld_peer_u32(P.partial_depth[q] + s2);
+                for (int q = 0; q < P.n_ranks; ++q) P.final_depth[q][s2] = sum;
+            }
+        }
+    }
+}
+
 }  // namespace fgfa

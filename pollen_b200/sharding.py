@@ -111,3 +111,93 @@ class ShardedDepth:
 
     def status(self) -> None:
         self.plan.status(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+
+class FusedShardedDepth:
+    """Per-rank engine with the exchange fused into the popcount kernel (kernel X,
+    ``k_uniq_exchange``): partial depth and the seen-bitmap live in symmetric (peer-mapped)
+    memory, every rank reduces its slice of the segment axis straight from its peers over
+    NVLink and stores the final slice into every rank's result buffer.  Needs <= 255 paths
+    in the whole graph (u8 uniq) and ``torch.distributed._symmetric_memory``.
+
+    ``rows_per_rank``: number of paths each rank holds (same list on every rank)."""
+
+    def __init__(self, local_start, local_end, n_segs: int, device, rows_per_rank, group=None, use_multicast=True):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from .binding import DepthPlan
+
+        self.torch, self.dist = torch, dist
+        self.device = device
+        self.n_segs = int(n_segs)
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.rows = [int(r) for r in rows_per_rank]
+        assert len(self.rows) == self.world and sum(self.rows) <= 255
+        assert len(local_start) == self.rows[self.rank]
+        self.n_local_steps = int(local_end[-1]) if len(local_end) else 0
+        self.plan = DepthPlan(local_start, local_end, n_segs, self.n_local_steps)
+        row_bytes = self.plan.bitmap_row_bytes
+        al = lambda x: (x + 255) // 256 * 256
+        self.off_partial = 0
+        self.off_bitmap = al(self.n_segs * 4)
+        self.off_final_depth = self.off_bitmap + al(row_bytes * max(1, max(self.rows)))
+        self.off_final_uniq = self.off_final_depth + al(self.n_segs * 4)
+        total = self.off_final_uniq + al(self.n_segs)
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        # NVLS multicast mapping of the same buffer, when the fabric offers one
+        import os
+
+        if os.environ.get("FGFA_MULTICAST", "1") == "0":
+            use_multicast = False
+        self.mc_ptr = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
+        self.plan.use_bitmap(self.ptrs[self.rank] + self.off_bitmap, row_bytes * max(1, self.rows[self.rank]))
+        self.bitmap_view = self.buf[self.off_bitmap: self.off_bitmap + row_bytes * max(1, self.rows[self.rank])]
+        self.depth = self.buf[self.off_final_depth: self.off_final_depth + 4 * self.n_segs].view(torch.int32)
+        self.uniq = self.buf[self.off_final_uniq: self.off_final_uniq + self.n_segs]
+        self.compact = True
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    @property
+    def exchange_bytes(self) -> int:
+        """NVLink bytes this rank moves per step (in + out)."""
+        n, w = self.n_segs, self.world
+        slice_segs = -(-n // w)
+        rows_remote = sum(self.rows) - self.rows[self.rank]
+        return (w - 1) * slice_segs * 4 + rows_remote * slice_segs // 8 + (w - 1) * slice_segs * 5
+
+    def results(self):
+        import numpy as np
+
+        d = self.depth.cpu().numpy().view(np.uint32).astype(np.uint64)
+        u = self.uniq.cpu().numpy().astype(np.uint64)
+        return d, u
+
+    def run(self, d_steps, stream=None) -> None:
+        from .binding import exchange_uniq_depth
+
+        torch = self.torch
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st):
+            self.plan.run_stream_only(d_steps, self.ptrs[self.rank] + self.off_partial, st.cuda_stream)
+            self.hdl.barrier(channel=0)                      # every rank's partials are complete
+            exchange_uniq_depth(
+                self.world, self.rank,
+                [p + self.off_bitmap for p in self.ptrs], self.rows,
+                [p + self.off_partial for p in self.ptrs],
+                [p + self.off_final_depth for p in self.ptrs],
+                [p + self.off_final_uniq for p in self.ptrs],
+                self.n_segs, st.cuda_stream,
+                multicast_base=self.mc_ptr, off_partial=self.off_partial,
+                off_final_depth=self.off_final_depth, off_final_uniq=self.off_final_uniq)
+            self.hdl.barrier(channel=1)                      # every rank's result slices have landed
+            self.bitmap_view.zero_()                         # clean seen-bits for the next run
+
+    def status(self) -> None:
+        self.plan.status(self.torch.cuda.current_stream(self.device).cuda_stream)

@@ -304,6 +304,43 @@ def test_sharded_partials_sum_to_the_whole(torch_cuda):
             assert (packed == ou).all()
 
 
+def test_fused_exchange_kernel_on_one_device(torch_cuda):
+    """Kernel X (popcount fused with the cross-rank reduce-scatter/all-gather) with all
+    "ranks" living on one GPU: each rank's slice launch reads every rank's partial depth and
+    bitmap rows and writes every rank's result buffers."""
+    torch = torch_cuda
+    from pollen_b200.binding import exchange_uniq_depth
+    for name, world in (("tinyE", 3), ("B", 4), ("tiny", 7)):
+        cfg = synth.CONFIGS[name]
+        steps, s, e = synth.make_graph(cfg)
+        rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+        parts = sharding.lpt_partition(e - s, world)
+        st = torch.cuda.current_stream().cuda_stream
+        plans, partial, bitmaps, fin_d, fin_u, keep = [], [], [], [], [], []
+        for part in parts:
+            ls_steps, ls, le = synth.make_graph(cfg, path_subset=part)
+            plan = pb.DepthPlan(ls, le, cfg.n_segs, int(le[-1]) if len(le) else 0)
+            bm = torch.zeros(plan.bitmap_row_bytes * max(1, len(part)), dtype=torch.uint8, device="cuda")
+            plan.use_bitmap(bm.data_ptr(), bm.numel())
+            pd = torch.empty(cfg.n_segs, dtype=torch.int32, device="cuda")
+            d_steps = _dev(torch, ls_steps) if len(ls_steps) else torch.zeros(4, dtype=torch.int32, device="cuda")
+            plan.run_stream_only(d_steps, pd.data_ptr(), st)
+            plan.status(st)
+            plans.append(plan); partial.append(pd); bitmaps.append(bm); keep.append(d_steps)
+            fin_d.append(torch.full((cfg.n_segs,), -1, dtype=torch.int32, device="cuda"))
+            fin_u.append(torch.full((cfg.n_segs,), 255, dtype=torch.uint8, device="cuda"))
+        for r in range(world):
+            exchange_uniq_depth(world, r, [b.data_ptr() for b in bitmaps], [len(p) for p in parts],
+                                [p.data_ptr() for p in partial], [t.data_ptr() for t in fin_d],
+                                [t.data_ptr() for t in fin_u], cfg.n_segs, st)
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert (fin_d[r].cpu().numpy().view(np.uint32) == od).all(), (name, r)
+            assert (fin_u[r].cpu().numpy() == ou).all(), (name, r)
+        for p in plans:
+            p.close()
+
+
 # ------------------------------------------------------------------- full size ------
 def test_full_size_config_C_vs_oracle_and_properties(torch_cuda):
     """BASELINE.json configs[2]: 5M segments, 90 paths, 400M steps (device-resident)."""
