@@ -45,6 +45,7 @@ constexpr size_t kDefaultBitmapBudget = 64ull << 20;  // stays resident in the 1
 // on B200 (the extra CTAs start as the first ones drain, which evens out the tail).
 constexpr int kBlocksPerSM = 5;
 constexpr int kGridPerSM = 10;
+constexpr int kPopMinBlocks = 4;       // kernel B register cap (measured, see profiles/)
 
 }  // namespace
 
@@ -151,7 +152,7 @@ int launch_popcount(fgfa_depth_plan* pl, uint32_t rows, uint32_t* d_uniq, bool a
     Q.accumulate = accumulate ? 1 : 0;
     Q.uniq_bytes = pl->uniq_bytes;
     const uint32_t grid = (pl->n_words + fgfa::kPopThreads - 1) / fgfa::kPopThreads;
-    fgfa::k_uniq_popcount<<<grid, fgfa::kPopThreads, 0, st>>>(Q);
+    fgfa::k_uniq_popcount<kPopMinBlocks><<<grid, fgfa::kPopThreads, 0, st>>>(Q);
     CU(cudaGetLastError());
     return FGFA_OK;
 }
@@ -413,7 +414,11 @@ int fgfa_exchange_uniq_depth(int n_ranks, int rank, const void* const* bitmaps, 
     if (X.w_hi > X.w_lo) {
         const uint32_t words = X.w_hi - X.w_lo;
         X.uniq_blocks = (words + fgfa::kXThreads - 1) / fgfa::kXThreads;
-        const uint32_t depth_blocks = (words * 8 + fgfa::kXThreads - 1) / fgfa::kXThreads;   // 4 segments per thread
+        uint32_t depth_blocks = (words * 8 + fgfa::kXThreads - 1) / fgfa::kXThreads;   // 4 segments per thread
+        if (const char* role = std::getenv("FGFA_X_ROLE")) {   // measurement only: run one role of kernel X
+            if (!std::strcmp(role, "uniq")) depth_blocks = 0;
+            else if (!std::strcmp(role, "depth")) { X.w_lo += 0; X.uniq_blocks = 0; }
+        }
         fgfa::k_uniq_exchange<<<X.uniq_blocks + depth_blocks, fgfa::kXThreads, 0, (cudaStream_t)cuda_stream>>>(X);
         CU(cudaGetLastError());
     }

@@ -357,7 +357,8 @@ struct PopcountParams {
 constexpr int kPopThreads = 128;
 constexpr int kPopRowsInFlight = 8;
 
-__global__ void __launch_bounds__(kPopThreads) k_uniq_popcount(PopcountParams P) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kPopThreads, MIN_BLOCKS) k_uniq_popcount(PopcountParams P) {
     __shared__ uint32_t tile[kPopThreads / 32][32][33];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kPopThreads + threadIdx.x;

@@ -163,25 +163,33 @@ int main(int argc, char** argv) {
     }
     {
         int pgrid = (n_words + kPopThreads - 1) / kPopThreads;
-        // populate bitmap once, then time popcount (it clears as it goes, so refill each rep)
+        // populate bitmap, then time popcount (it clears as it goes, so refill each rep)
+        auto time_pop = [&](const char* nm, auto&& launch) {
+            float best = 1e30f;
+            for (int r = 0; r < reps; ++r) {
+                k_step_stream_direct<kModeSeenOnly, 1><<<sms * 8, kThreads>>>(P);
+                CK(cudaEventRecord(e0));
+                launch();
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                best = std::min(best, ms);
+            }
+            printf("%-34s best %8.3f ms\n", nm, best);
+        };
+        time_pop("uniq popcount <1>", [&] { k_uniq_popcount<1><<<pgrid, kPopThreads>>>(Q); });
+        time_pop("uniq popcount <4>", [&] { k_uniq_popcount<4><<<pgrid, kPopThreads>>>(Q); });
+        time_pop("uniq popcount <6>", [&] { k_uniq_popcount<6><<<pgrid, kPopThreads>>>(Q); });
+        time_pop("uniq popcount <8>", [&] { k_uniq_popcount<8><<<pgrid, kPopThreads>>>(Q); });
+        time_pop("uniq popcount <12>", [&] { k_uniq_popcount<12><<<pgrid, kPopThreads>>>(Q); });
         float best = 1e30f;
-        for (int r = 0; r < reps; ++r) {
-            k_step_stream_direct<kModeSeenOnly, 1><<<sms * 8, kThreads>>>(P);
-            CK(cudaEventRecord(e0));
-            k_uniq_popcount<<<pgrid, kPopThreads>>>(Q);
-            CK(cudaEventRecord(e1));
-            CK(cudaEventSynchronize(e1));
-            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-            best = std::min(best, ms);
-        }
-        printf("%-34s best %8.3f ms\n", "uniq popcount", best);
         // full pipeline: memset + A + B
         float sum = 0; best = 1e30f;
         for (int r = 0; r < reps + 2; ++r) {
             CK(cudaEventRecord(e0));
             CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
             k_step_stream_direct<kModeDepthAndSeen, 1><<<sms * 8, kThreads>>>(P);
-            k_uniq_popcount<<<pgrid, kPopThreads>>>(Q);
+            k_uniq_popcount<4><<<pgrid, kPopThreads>>>(Q);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -244,7 +252,7 @@ int main(int argc, char** argv) {
                 CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(d_depth, 0, (size_t)cfg.n_segs * 4));
                 if (use_merged) k_step_stream_merged<5, kSeenDeferred><<<sms * 10, kThreads, stream_smem_bytes(kSeenDeferred)>>>(S); else if (use_wagg) k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); else run_ft(bps);
-                k_uniq_popcount<<<pgrid, kPopThreads>>>(Q2);
+                k_uniq_popcount<4><<<pgrid, kPopThreads>>>(Q2);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
                 CK(cudaGetLastError());
