@@ -245,10 +245,12 @@ def main():
     if sampler:
         sampler.start()
     barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record(stream)
     for k in range(args.steps):
         eng.plan.set_probe(probes[k][0].cuda_event, probes[k][1].cuda_event)
         eng.run(d_steps, stream)
+        marks[k].record(stream)
     ev1.record(stream)
     barrier()
     eng.status()
@@ -259,6 +261,8 @@ def main():
         dist.all_reduce(ms_kernel, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms_total.item()) / args.steps
     value = cfg.n_steps / (ms_per_step * 1e-3)
+    per_step = [(ev0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(args.steps)]   # this rank
+    step_stats = {"median_ms": statistics.median(per_step), "best_ms": min(per_step), "worst_ms": max(per_step)}
 
     # checksum of the result (sum of depth must equal the number of steps)
     depth_sum = int(eng.depth.to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
@@ -310,7 +314,7 @@ def main():
     eng.status()
     split = {"depth_only_ms_per_step": depth_only_ms, "depth_only_steps_per_s": cfg.n_steps / (depth_only_ms * 1e-3),
              "exchange_ms": allreduce_ms, "exchange_bytes_per_rank": eng.exchange_bytes if world > 1 else 0,
-             "stream_kernel_ms": k_ms}
+             "stream_kernel_ms": k_ms, "per_step_rank0": step_stats}
 
     # ---- end to end: host buffers in, host results out ---------------------------------
     e2e_steps = max(1, args.e2e_steps)

@@ -156,6 +156,34 @@ def test_overlapping_and_unordered_spans():
     _check_vs_oracle(steps, start, end, n_segs)
 
 
+def test_one_giant_path_and_many_tiny_ones():
+    """SURVEY §8(d) adversarial shape: one path holds almost every step, hundreds of paths of
+    1-40 steps follow (more paths than a u8 counter could hold, several bitmap batches)."""
+    rng = np.random.default_rng(17)
+    n_segs = 40_003
+    lens = np.concatenate([[1_500_000], rng.integers(1, 41, 700)])
+    end = np.cumsum(lens).astype(np.uint32)
+    start = (end - lens).astype(np.uint32)
+    walk = (np.cumsum(rng.integers(0, 3, int(end[-1]))) % n_segs).astype(np.uint32)
+    walk[lens[0]:] = rng.integers(0, 60, walk.size - lens[0])      # all the tiny paths share 60 segments
+    steps = (walk << 1) | rng.integers(0, 2, walk.size, dtype=np.uint32)
+    od, ou = _check_vs_oracle(steps, start, end, n_segs)
+    assert int(ou.max()) > 255
+    # the same graph through a plan whose bitmap holds only 64 paths at a time
+    import torch
+    row_bytes = ((n_segs + 31) // 32 + 31) // 32 * 32 * 4
+    plan = pb.DepthPlan(start, end, n_segs, int(end[-1]), bitmap_budget_bytes=64 * row_bytes)
+    out = torch.empty(2 * n_segs, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    plan.run(_dev(torch, steps), out[:n_segs], out[n_segs:], st)
+    plan.status(st)
+    g = out.cpu().numpy().view(np.uint32)
+    assert plan.launches(True) == 2 * 11 and (g[:n_segs] == od).all() and (g[n_segs:] == ou).all()
+    # LPT keeps the giant alone
+    parts = sharding.lpt_partition(lens, 4)
+    assert [0] in parts
+
+
 def test_errors_where_the_reference_panics():
     steps = np.array([0, 2, 8, 6], np.uint32)
     with pytest.raises(pb.DepthError) as e:
