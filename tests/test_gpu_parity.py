@@ -165,7 +165,7 @@ def test_one_giant_path_and_many_tiny_ones():
     end = np.cumsum(lens).astype(np.uint32)
     start = (end - lens).astype(np.uint32)
     walk = (np.cumsum(rng.integers(0, 3, int(end[-1]))) % n_segs).astype(np.uint32)
-    walk[lens[0]:] = rng.integers(0, 60, walk.size - lens[0])      # all the tiny paths share 60 segments
+    walk[lens[0]:] = rng.integers(0, 20, walk.size - lens[0])      # all the tiny paths share 20 segments
     steps = (walk << 1) | rng.integers(0, 2, walk.size, dtype=np.uint32)
     od, ou = _check_vs_oracle(steps, start, end, n_segs)
     assert int(ou.max()) > 255
