@@ -132,14 +132,20 @@ constexpr uint32_t kFiller = 0xFFFFFFFFu;   // never a valid handle: segment ids
 //                neighbouring threads' k-th runs fall into the same 32-byte bitmap sector
 //                (a sector covers 256 segments, a thread ~19), so the L2 sees one request
 //                per sector instead of one per run.  No barrier, no atomics on shared memory.
-//   kSeenWindow  thread-level runs are first OR-ed into a block-wide shared-memory window
-//                (direct-mapped by bitmap-word index, one tag per 32-byte bitmap sector),
-//                then every touched sector is flushed with ONE coalesced RED.OR request.
-//                A chunk re-visits the same bitmap sectors many times (a sector covers 256
-//                segments), so this cuts the L2 reduction sectors of the seen-bits ~3-4x.
+//   kSeenWindow  for looping paths (tandem repeats, config E).  Thread-level runs are first
+//                OR-ed into a block-wide shared-memory window (direct-mapped by bitmap-word
+//                index, one tag per 32-byte bitmap sector), then every touched sector is
+//                flushed with ONE coalesced RED.OR request.  In addition the depth counters
+//                of a chunk whose segments span < kCacheSegs are accumulated in a
+//                shared-memory cache that PERSISTS across the block's chunks as long as they
+//                stay inside the same segment window (a loop does), and is flushed with
+//                coalesced RED.ADDs when the window moves or the kernel ends: the hot
+//                segments' adds never serialise in L2.
 enum SeenMode : int { kSeenNone = 0, kSeenDirect = 1, kSeenWindow = 2, kSeenDeferred = 3 };
 
-constexpr uint32_t kWinWords = 4096;              // window: 4096 bitmap words = 131072 segments
+constexpr uint32_t kCacheSegs = 8192;             // kSeenWindow: depth counters cached in shared memory
+constexpr uint32_t kWinShift = 11;
+constexpr uint32_t kWinWords = 1u << kWinShift;   // window: 2048 bitmap words = 65536 segments
 constexpr uint32_t kWinGroups = kWinWords / 8;    // one tag per bitmap sector (8 words)
 constexpr uint32_t kTagEmpty = 0xFFFFFFFFu;
 
@@ -147,7 +153,7 @@ constexpr int kRunSlots = 4;                      // kSeenDeferred: parked runs 
 
 __host__ __device__ constexpr size_t stream_smem_bytes(int seen_mode) {
     return 2 * (size_t)kChunk * 4 +
-           (seen_mode == kSeenWindow ? (size_t)kWinWords * 4 + kWinGroups * 4 + kWinGroups * 4 + 16 : 0) +
+           (seen_mode == kSeenWindow ? (size_t)kWinWords * 4 + kWinGroups * 4 + kWinGroups * 4 + 16 + (size_t)kCacheSegs * 4 : 0) +
            (seen_mode == kSeenDeferred ? (size_t)kRunSlots * kThreads * 8 : 0);
 }
 
@@ -168,12 +174,15 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
     uint32_t* const s_bits = reinterpret_cast<uint32_t*>(smem_dyn + 2 * (kChunk / 4));   // [kWinWords]
     uint32_t* const s_tag = s_bits + kWinWords;                                          // [kWinGroups]
     uint32_t* const s_list = s_tag + kWinGroups;                                         // [kWinGroups]
-    uint32_t* const s_count = s_list + kWinGroups;
+    uint32_t* const s_count = s_list + kWinGroups;                                       // [0] list length, [1] min, [2] max
+    uint32_t* const s_cnt = s_count + 4;                                                 // [kCacheSegs]
+    uint32_t cache_base = kFiller;               // first segment of the cached depth window (block-uniform)
     uint2* const s_runs = reinterpret_cast<uint2*>(smem_dyn + 2 * (kChunk / 4)) + threadIdx.x;   // [kRunSlots][kThreads]
     if (SEEN_MODE == kSeenWindow) {
         for (uint32_t i = threadIdx.x; i < kWinWords; i += kThreads) s_bits[i] = 0u;
         for (uint32_t i = threadIdx.x; i < kWinGroups; i += kThreads) s_tag[i] = kTagEmpty;
-        if (threadIdx.x == 0) *s_count = 0u;
+        for (uint32_t i = threadIdx.x; i < kCacheSegs; i += kThreads) s_cnt[i] = 0u;
+        if (threadIdx.x == 0) { s_count[0] = 0u; s_count[1] = 0xFFFFFFFFu; s_count[2] = 0u; }
     }
     const uint64_t pol = make_evict_first_policy();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -225,6 +234,36 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
         __syncthreads();
 
         const uint4* buf = s_steps[b];
+        bool cached = false;                     // block-uniform: this chunk's depth adds go to the cache
+        if (SEEN_MODE == kSeenWindow) {
+            // chunk-wide min / max handle (fillers and out-of-range ids make the chunk uncacheable)
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(buf) + p3_off;
+            uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) {
+                const uint32_t v = w[i * kThreads];
+                lo = min(lo, v);
+                hi = max(hi, v);
+            }
+            lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+            hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+            if (lane == 0) { atomicMin(&s_count[1], lo); atomicMax(&s_count[2], hi); }
+            __syncthreads();
+            const uint32_t seg_lo = s_count[1] >> 1, seg_hi = s_count[2] >> 1;
+            if (s_count[2] < seg_limit && seg_hi - (seg_lo & ~7u) < kCacheSegs) {
+                cached = true;
+                if (cache_base == kFiller || seg_lo < cache_base || seg_hi >= cache_base + kCacheSegs) {
+                    if (cache_base != kFiller) {     // the window moves: flush the old one
+                        for (uint32_t i = tid; i < kCacheSegs; i += kThreads) {
+                            const uint32_t v = s_cnt[i];
+                            if (v) { red_add_u32(depth_ptr + cache_base + i, v); s_cnt[i] = 0u; }
+                        }
+                        __syncthreads();
+                    }
+                    cache_base = seg_lo & ~7u;
+                }
+            }
+        }
         // ---- pass 2: thread order -- one RED.OR per run of steps in the same bitmap word ----
         if (WITH_SEEN) {
             uint32_t* __restrict__ row = P.bitmap + (size_t)(cur.path - P.path_lo) * P.words_per_row;
@@ -253,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
                             else red_or_b32(row + w, acc);
                             ++cnt;
                         } else if (SEEN_MODE == kSeenWindow) {
-                            const uint32_t g = (w >> 3) & (kWinGroups - 1), tag = w >> 12;
+                            const uint32_t g = (w >> 3) & (kWinGroups - 1), tag = w >> kWinShift;
                             uint32_t t = s_tag[g];
                             if (t == kTagEmpty) {
                                 t = atomicCAS(&s_tag[g], kTagEmpty, tag);
@@ -297,10 +336,18 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
             uint32_t hh[kItems];
 #pragma unroll
             for (int i = 0; i < kItems; ++i) hh[i] = w[i * kThreads];
+            if (cached) {                        // every handle is valid and inside the cached window
 #pragma unroll
-            for (int i = 0; i < kItems; ++i) {
-                if (hh[i] < seg_limit) red_add_u32(depth_ptr + (hh[i] >> 1), 1u);
-                else if (!WITH_SEEN && hh[i] != kFiller) *P.err = 1u;
+                for (int i = 0; i < kItems; ++i) {
+                    const uint32_t a = (uint32_t)__cvta_generic_to_shared(s_cnt + ((hh[i] >> 1) - cache_base));
+                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) {
+                    if (hh[i] < seg_limit) red_add_u32(depth_ptr + (hh[i] >> 1), 1u);
+                    else if (!WITH_SEEN && hh[i] != kFiller) *P.err = 1u;
+                }
             }
         }
         if (SEEN_MODE == kSeenWindow) {
@@ -314,20 +361,26 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
                 const uint32_t g = on ? s_list[i >> 3] : 0u, slot = (g << 3) | (i & 7u);
                 const uint32_t v = on ? s_bits[slot] : 0u, tag = s_tag[g];
                 if (v) {
-                    red_or_b32(row + ((tag << 12) | slot), v);
+                    red_or_b32(row + ((tag << kWinShift) | slot), v);
                     s_bits[slot] = 0u;
                 }
                 __syncwarp();                            // every lane has read the tag
                 if (on && (i & 7u) == 0u) s_tag[g] = kTagEmpty;
             }
             __syncthreads();
-            if (tid == 0) *s_count = 0u;
+            if (tid == 0) { s_count[0] = 0u; s_count[1] = 0xFFFFFFFFu; s_count[2] = 0u; }
         } else {
             __syncthreads();                     // buffer b is free for the prefetch after next
         }
         cur = nxt;
         nxt = nxt2;
         b ^= 1;
+    }
+    if (SEEN_MODE == kSeenWindow && cache_base != kFiller) {   // flush what is still cached
+        for (uint32_t i = tid; i < kCacheSegs; i += kThreads) {
+            const uint32_t v = s_cnt[i];
+            if (v) red_add_u32(depth_ptr + cache_base + i, v);
+        }
     }
 }
 
