@@ -11,6 +11,10 @@
 //   kernel B  (k_uniq_popcount) sums the bitmap rows column-wise with bit-sliced
 //             counters: uniq[seg] = #rows with bit seg set (depth.rs:32), and clears
 //             the rows it consumed so the next run starts from a zero bitmap.
+//   kernel C  (k_path_measure) the per-path weighted sums of path-depth mode
+//             (`measure_path`, depth.rs:116-131).
+//   kernel X  (k_uniq_exchange) kernel B fused with the multi-GPU reduce-scatter /
+//             all-gather of depth and uniq over NVLink peer memory.
 //
 // Work decomposition: a *chunk* is up to kChunk consecutive steps of ONE path
 // (a chunk never straddles two paths because the bitmap row depends on the path);
