@@ -153,7 +153,7 @@ constexpr uint32_t kWinWords = 1u << kWinShift;   // window: 2048 bitmap words =
 constexpr uint32_t kWinGroups = kWinWords / 8;    // one tag per bitmap sector (8 words)
 constexpr uint32_t kTagEmpty = 0xFFFFFFFFu;
 
-constexpr int kRunSlots = 4;                      // kSeenDeferred: parked runs per thread per chunk
+constexpr int kRunSlots = 4;                      // kSeenDeferred: parked runs per thread per chunk (3, 4, 6 measure alike)
 
 __host__ __device__ constexpr size_t stream_smem_bytes(int seen_mode) {
     return 2 * (size_t)kChunk * 4 +

@@ -112,6 +112,20 @@ int main(int argc, char** argv) {
     printf("device %s, %d SMs, chunks=%u, bitmap %.1f MB\n", prop.name, sms, n_chunks,
            (double)cfg.n_paths * wpr * 4 / 1e6);
 
+    if (const char* pv = getenv("UBENCH_PERSIST")) {
+        // experiment: pin the depth table (and, with 2, the bitmap too) in L2 with a persisting window
+        printf("persistingL2CacheMaxSize = %.1f MB, accessPolicyMaxWindowSize = %.1f MB\n",
+               prop.persistingL2CacheMaxSize / 1e6, prop.accessPolicyMaxWindowSize / 1e6);
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize));
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = atoi(pv) == 2 ? (void*)d_bitmap : (void*)d_depth;
+        av.accessPolicyWindow.num_bytes = std::min<size_t>(atoi(pv) == 2 ? (size_t)cfg.n_paths * wpr * 4 : (size_t)cfg.n_segs * 4,
+                                                           prop.accessPolicyMaxWindowSize);
+        av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(0, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
