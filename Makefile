@@ -37,7 +37,9 @@ bin/fgfa: $(CSRC)/fgfa_main.cpp $(LIBDIR)/libflatgfa.so
 oracle:
 	$(MAKE) -C oracle
 
-tools: build/ubench
+tools: build/ubench build/sort_dedup_probe
+build/sort_dedup_probe: tools/sort_dedup_probe.cu $(CSRC)/synth.cpp oracle/depth_oracle.c build/ubench
+	$(NVCC) $(ARCH) -O3 -std=c++17 tools/sort_dedup_probe.cu build/depth_oracle.o build/synth.o -o $@
 build/ubench: tools/ubench.cu tools/experimental_kernels.cuh $(CSRC)/depth_kernels.cuh $(CSRC)/synth.cpp oracle/depth_oracle.c
 	@mkdir -p build
 	$(CC) -O3 -c oracle/depth_oracle.c -o build/depth_oracle.o
