@@ -68,6 +68,8 @@ struct fgfa_depth_plan {
     cudaEvent_t probe_before = nullptr, probe_after = nullptr;   // one-shot measurement hook
     uint32_t next_path = 0;                // begin/feed/finish cursor
     bool uniq_started = false;
+    bool bitmap_dirty = false;             // seen-bits recorded that no kernel B has consumed yet
+    int feed_mode = -1;                    // -1: no feed yet; 0: depth only; 1: depth + uniq (fixed per begin..finish)
 };
 
 namespace {
@@ -281,8 +283,13 @@ int fgfa_depth_plan_begin(fgfa_depth_plan_t* pl, uint32_t* d_depth, void* cuda_s
     if (!pl || (!d_depth && pl->n_segs)) return fail(FGFA_ERR_INVALID_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (pl->n_segs) CU(cudaMemsetAsync(d_depth, 0, (size_t)pl->n_segs * 4, st));  // depth.rs:17 vec![0; n]
+    if (pl->bitmap_dirty && pl->own_bitmap) {   // an earlier begin..finish run was abandoned half way
+        CU(cudaMemsetAsync(pl->d_bitmap, 0, (size_t)pl->words_per_row * 4 * pl->rows_per_batch, st));
+        pl->bitmap_dirty = false;
+    }
     pl->next_path = 0;
     pl->uniq_started = false;
+    pl->feed_mode = -1;
     return FGFA_OK;
 }
 
@@ -299,17 +306,22 @@ int fgfa_depth_plan_feed(fgfa_depth_plan_t* pl, const uint32_t* d_steps, uint32_
         if (rc) return rc;
     }
     const bool with_seen = d_uniq != nullptr;
+    if (pl->feed_mode >= 0 && pl->feed_mode != (int)with_seen)
+        return fail(FGFA_ERR_INVALID_ARG, "d_uniq must be given to every feed of a run or to none");
+    pl->feed_mode = (int)with_seen;
     uint32_t lo = path_lo;
     while (lo < path_hi) {
         const uint32_t batch_end = std::min<uint64_t>(pl->n_paths, ((uint64_t)lo / pl->rows_per_batch + 1) * pl->rows_per_batch);
         const uint32_t hi = std::min(path_hi, batch_end);
         int rc = launch_stream(pl, base, lo, hi, d_depth, with_seen, st);
         if (rc) return rc;
+        if (with_seen) pl->bitmap_dirty = true;
         if (with_seen && hi == batch_end) {  // this bitmap batch is complete: fold it into uniq
             const uint32_t batch_start = (lo / pl->rows_per_batch) * pl->rows_per_batch;
             rc = launch_popcount(pl, batch_end - batch_start, d_uniq, pl->uniq_started, st);
             if (rc) return rc;
             pl->uniq_started = true;
+            pl->bitmap_dirty = false;
         }
         lo = hi;
     }
@@ -320,6 +332,8 @@ int fgfa_depth_plan_feed(fgfa_depth_plan_t* pl, const uint32_t* d_steps, uint32_
 int fgfa_depth_plan_finish(fgfa_depth_plan_t* pl, uint32_t* d_uniq, void* cuda_stream) {
     if (!pl) return fail(FGFA_ERR_INVALID_ARG, "null plan");
     if (pl->next_path != pl->n_paths) return fail(FGFA_ERR_INVALID_ARG, "not all paths were fed");
+    if (pl->feed_mode >= 0 && pl->feed_mode != (int)(d_uniq != nullptr))
+        return fail(FGFA_ERR_INVALID_ARG, "d_uniq must match the feeds of this run");
     if (d_uniq && !pl->uniq_started && pl->n_segs)  // no paths at all: uniq is all zero
         CU(cudaMemsetAsync(d_uniq, 0, (size_t)pl->n_segs * pl->uniq_bytes, (cudaStream_t)cuda_stream));
     return FGFA_OK;

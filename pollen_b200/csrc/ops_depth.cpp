@@ -65,7 +65,7 @@ uint64_t fnv1a(const uint32_t* a, size_t n, uint64_t h) {
     return h;
 }
 
-int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, bool want_uniq, size_t aux_bytes = 0) {
+int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, size_t aux_bytes = 0) {
     int dev = 0;
     CUH(cudaGetDevice(&dev));
     if (w.device != dev) {
@@ -99,7 +99,6 @@ int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, bool want_
         CUH(cudaMalloc(&w.aux, aux_bytes));
         w.aux_cap = aux_bytes;
     }
-    (void)want_uniq;
     return FGFA_OK;
 }
 
@@ -137,7 +136,7 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
     struct Releaser { Workspace& w; bool on; ~Releaser() { if (on) w.release(); } } releaser{W, !keep};
 
     const bool want_uniq = uniq_out != nullptr;
-    int rc = ensure_workspace(W, n_steps, n_segs, want_uniq);
+    int rc = ensure_workspace(W, n_steps, n_segs);
     if (rc) return rc;
     const uint64_t key[4] = {n_paths, n_segs, n_steps,
                              fnv1a(h_span_end, n_paths, fnv1a(h_span_start, n_paths, 0xCBF29CE484222325ull))};
@@ -214,7 +213,7 @@ int fgfa_path_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint3
 
     const size_t sums_bytes = std::max<size_t>((size_t)n_paths * 16, 16);
     const size_t scratch_bytes = std::max<size_t>((size_t)n_segs * 8, 16);
-    int rc = ensure_workspace(W, n_steps, n_segs, false, scratch_bytes + sums_bytes);
+    int rc = ensure_workspace(W, n_steps, n_segs, scratch_bytes + sums_bytes);
     if (rc) return rc;
     const uint64_t key[4] = {n_paths, n_segs, n_steps,
                              fnv1a(h_span_end, n_paths, fnv1a(h_span_start, n_paths, 0xCBF29CE484222325ull))};

@@ -281,6 +281,44 @@ def test_both_seen_bit_strategies(torch_cuda, mode, monkeypatch):
     _check_vs_oracle(steps, np.array([0, 20_000], np.uint32), np.array([20_000, 40_000], np.uint32), n_segs)
 
 
+def test_workspace_lifecycle_and_feed_contract(torch_cuda, monkeypatch):
+    """The host-buffer entry points cache their staging between calls; releasing it, or
+    disabling the cache with FGFA_WORKSPACE=0, must not change results.  A begin..finish run
+    takes d_uniq on every feed or on none."""
+    torch = torch_cuda
+    lib = pb.lib()
+    for name in ("tiny", "tinyE", "tiny"):          # shrink, grow, same plan key again
+        cfg = synth.CONFIGS[name]
+        steps, s, e = synth.make_graph(cfg)
+        _check_vs_oracle(steps, s, e, cfg.n_segs)
+        lib.fgfa_release_workspace()
+        _check_vs_oracle(steps, s, e, cfg.n_segs)
+    monkeypatch.setenv("FGFA_WORKSPACE", "0")
+    _check_vs_oracle(steps, s, e, cfg.n_segs)
+    monkeypatch.delenv("FGFA_WORKSPACE")
+    plan = pb.DepthPlan(s, e, cfg.n_segs, cfg.n_steps)
+    d_steps = _dev(torch, steps)
+    out = torch.empty(2 * cfg.n_segs, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    plan.begin(out[: cfg.n_segs], st)
+    plan.feed(d_steps, 0, 2, out[: cfg.n_segs], out[cfg.n_segs:], st)
+    with pytest.raises(pb.DepthError):
+        plan.feed(d_steps, 2, cfg.n_paths, out[: cfg.n_segs], None, st)        # uniq dropped mid-run
+    with pytest.raises(pb.DepthError):
+        plan.feed(d_steps, 3, cfg.n_paths, out[: cfg.n_segs], out[cfg.n_segs:], st)   # gap in the path order
+    with pytest.raises(pb.DepthError):
+        plan.finish(out[cfg.n_segs:], st)                                       # not all paths fed
+    # a fresh run resets the cursor and must not see the seen-bits the abandoned run left
+    # behind: run it on DIFFERENT steps (same spans) to prove that
+    steps2 = np.roll(steps, 12345) ^ np.uint32(2)
+    steps2 = np.minimum(steps2, np.uint32(2 * cfg.n_segs - 1))
+    plan.run(_dev(torch, steps2), out[: cfg.n_segs], out[cfg.n_segs:], st)
+    plan.status(st)
+    rc, od, ou = O.depth_with_uniq(steps2, s, e, cfg.n_segs)
+    g = out.cpu().numpy().view(np.uint32)
+    assert rc == 0 and (g[: cfg.n_segs] == od).all() and (g[cfg.n_segs:] == ou).all()
+
+
 def test_misaligned_device_pointer_and_one_shot_device_abi(torch_cuda):
     torch = torch_cuda
     cfg = synth.CONFIGS["tiny"]
