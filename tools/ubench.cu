@@ -234,11 +234,17 @@ int main(int argc, char** argv) {
         time_it("depth-only pairs(+2 even tid) g=8xSM", [&] { k_step_stream_direct<kModeDepthPairs, 1><<<sms * 8, kThreads>>>(P); }, false);
         const size_t smD = stream_smem_bytes(kSeenDirect), smW = stream_smem_bytes(kSeenWindow);
         CK(cudaFuncSetAttribute(k_step_stream_merged<8, kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smW));
+        CK(cudaFuncSetAttribute(k_step_stream_merged<2, kSeenDeferred>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_step_stream_merged<3, kSeenDeferred>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_step_stream_merged<4, kSeenDeferred>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_step_stream_merged<5, kSeenDeferred>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CK(cudaFuncSetAttribute(k_step_stream_merged<4, kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smW));
         time_it("merged direct-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenDirect><<<sms * 4, kThreads, smD>>>(S); }, true);
         time_it("merged direct-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenDirect><<<sms * 8, kThreads, smD>>>(S); }, true);
         const size_t smF = stream_smem_bytes(kSeenDeferred);
         time_it("merged deferred-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenDeferred><<<sms * 4, kThreads, smF>>>(S); }, true);
+        time_it("merged deferred-OR <2> grid 4x", [&] { k_step_stream_merged<2, kSeenDeferred><<<sms * 4, kThreads, smF>>>(S); }, true);
+        time_it("merged deferred-OR <3> grid 6x", [&] { k_step_stream_merged<3, kSeenDeferred><<<sms * 6, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR <4> grid 8x", [&] { k_step_stream_merged<4, kSeenDeferred><<<sms * 8, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR <5> grid 5x", [&] { k_step_stream_merged<5, kSeenDeferred><<<sms * 5, kThreads, smF>>>(S); }, true);
         time_it("deferred-OR P2=8 <5> grid 10x", [&] { k_step_stream_merged<5, kSeenDeferred, 8><<<sms * 10, kThreads, smF>>>(S); }, true);
