@@ -89,6 +89,24 @@ void gen_skewed(uint32_t* out, uint64_t len, uint32_t n_segs, uint64_t seed, uin
     }
 }
 
+// Kind 3: what an HPRC-style graph looks like after `odgi sort`: every haplotype walks the
+// node ids almost monotonically, taking one side of small bubbles (skip 1 segment w.p. 10 %,
+// skip 2-8 w.p. 1 %) and re-entering at a random place when it runs off the end.  Not a
+// BASELINE.json config; used to show how the kernels behave on dense, sorted walks.
+void gen_sorted_haplotype(uint32_t* out, uint64_t len, uint32_t n_segs, uint64_t seed) {
+    SplitMix64 rng(seed);
+    uint32_t cur = (uint32_t)(rng.next() % n_segs);
+    for (uint64_t i = 0; i < len; ++i) {
+        uint64_t r = rng.next();
+        uint32_t rev = ((uint32_t)r & 0xFFFF) < kRevThresh;
+        out[i] = (cur << 1) | rev;
+        uint32_t c = (uint32_t)(r >> 16) & 0xFFFF, hi = (uint32_t)(r >> 32);
+        uint32_t adv = c < 58327 ? 1u : c < 64881 ? 2u : 3u + hi % 7u;   // 89 % / 10 % / 1 %
+        cur += adv;
+        if (cur >= n_segs) cur = (uint32_t)(rng.next() % n_segs);
+    }
+}
+
 void gen_uniform(uint32_t* out, uint64_t len, uint32_t n_segs, uint64_t seed) {
     SplitMix64 rng(seed);
     for (uint64_t i = 0; i < len; ++i) {
@@ -131,7 +149,7 @@ int fgfa_synth_spans(uint32_t n_paths, uint64_t n_steps, uint32_t jitter_pct, ui
 }
 
 // kind 0: haplotype walk (configs B/C); 1: skewed looping paths (config E);
-// 2: uniform-random segment ids (adversarial, worst L2 locality).
+// 2: uniform-random segment ids (adversarial, worst L2 locality); 3: sorted haplotype walks.
 int fgfa_synth_steps(int kind, uint32_t n_segs, uint32_t n_paths, const uint32_t* span_start,
                      const uint32_t* span_end, uint64_t seed, uint32_t* steps_out, int n_threads) {
     if (n_segs == 0 || n_segs > 0x7FFFFFFFu) return -1;
@@ -146,6 +164,7 @@ int fgfa_synth_steps(int kind, uint32_t n_segs, uint32_t n_paths, const uint32_t
             uint64_t pseed = seed + p;
             if (kind == 0) gen_walk(out, len, n_segs, pseed);
             else if (kind == 1) gen_skewed(out, len, n_segs, pseed, p, seed);
+            else if (kind == 3) gen_sorted_haplotype(out, len, n_segs, pseed);
             else gen_uniform(out, len, n_segs, pseed);
         }
     };
@@ -165,6 +184,7 @@ int fgfa_synth_path(int kind, uint32_t n_segs, uint64_t len, uint64_t graph_seed
     const uint64_t pseed = graph_seed + path_idx;
     if (kind == 0) gen_walk(out, len, n_segs, pseed);
     else if (kind == 1) gen_skewed(out, len, n_segs, pseed, path_idx, graph_seed);
+    else if (kind == 3) gen_sorted_haplotype(out, len, n_segs, pseed);
     else gen_uniform(out, len, n_segs, pseed);
     return 0;
 }

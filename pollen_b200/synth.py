@@ -13,7 +13,7 @@ _LIB_PATH = os.path.join(_HERE, "lib", "libfgfa_synth.so")
 _lib = None
 
 SEED = 0xB1011054
-KIND_WALK, KIND_SKEWED, KIND_UNIFORM = 0, 1, 2
+KIND_WALK, KIND_SKEWED, KIND_UNIFORM, KIND_SORTED = 0, 1, 2, 3
 
 
 @dataclass(frozen=True)
@@ -39,6 +39,8 @@ CONFIGS = {
                 "skewed synthetic: 8 long looping paths, hot 4096-segment windows"),
     # adversarial extra: uniform-random segment ids
     "U": Config("U", 5_000_000, 90, 400_000_000, KIND_UNIFORM, 20, "uniform-random segment ids"),
+    # not in BASELINE.json: dense, id-sorted haplotype walks (what `odgi sort`ed HPRC graphs look like)
+    "R": Config("R", 5_000_000, 90, 400_000_000, KIND_SORTED, 20, "sorted haplotype walks, 5M segments, 90 paths, 400M steps"),
     # small shapes for tests
     "tiny": Config("tiny", 5_000, 7, 100_003, KIND_WALK, 30, "test-sized haplotype walk"),
     "tinyE": Config("tinyE", 20_000, 5, 300_007, KIND_SKEWED, 10, "test-sized skewed loops"),

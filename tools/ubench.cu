@@ -45,6 +45,7 @@ int main(int argc, char** argv) {
     else if (which == "E") cfg = {"E", 5000000, 8, 400000000ull, 1, 0};
     else if (which == "U") cfg = {"U", 5000000, 90, 400000000ull, 2, 20};
     else if (which == "S") cfg = {"S", 5000, 7, 100003ull, 0, 30};
+    else if (which == "R") cfg = {"R", 5000000, 90, 400000000ull, 3, 20};
     else { fprintf(stderr, "unknown cfg\n"); return 2; }
 
     int n_threads = (int)std::thread::hardware_concurrency();
