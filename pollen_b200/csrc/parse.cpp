@@ -1,7 +1,10 @@
 #include "parse.hpp"
 
+#include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace flatgfa {
@@ -136,20 +139,39 @@ struct Builder {
         const Handle to = Handle::make(seg_ids.get(to_seg), to_fwd);
         flat.add_link(from, to, overlap);
     }
-    void path(const uint8_t* line, size_t n) {   // gfaline.rs:88-100; parse.rs:149-159
-        Cursor c = body(line, n);
-        Cursor name = parse_field(c);
-        Cursor steps = parse_field(c);
-        std::vector<std::vector<AlignOp>> overlaps = parse_maybe_overlap_list(c);
-        if (!c.empty()) throw Error("expected end of line");
-        const uint32_t start = HeapGFAStore::id(flat.steps.size());
-        const size_t used = parse_steps(steps.p, steps.n, [&](uint64_t seg, bool fwd) {
-            flat.steps.push_back(Handle::make(seg_ids.get(seg), fwd));
-        });
-        if (used != steps.n) throw Error("malformed step list");   // parse.rs:155 assert
-        const Span span{start, HeapGFAStore::id(flat.steps.size())};
-        flat.add_path(name.p, name.n, span, overlaps);
+    // A P line parsed but not yet added to the store: the step list tokenisation (the bulk
+    // of a pangenome GFA) only reads the finished segment-name map, so many lines can be
+    // tokenised concurrently and then added in file order.
+    struct ParsedPath {
+        Cursor name{nullptr, 0};
+        std::vector<Handle> steps;
+        std::vector<std::vector<AlignOp>> overlaps;
+        std::string error;                 // non-empty: what the reference would have failed with
+    };
+    ParsedPath parse_path(const uint8_t* line, size_t n) const {   // gfaline.rs:88-100; parse.rs:149-156
+        ParsedPath out;
+        try {
+            Cursor c = body(line, n);
+            out.name = parse_field(c);
+            Cursor steps = parse_field(c);
+            out.overlaps = parse_maybe_overlap_list(c);
+            if (!c.empty()) throw Error("expected end of line");
+            out.steps.reserve(steps.n / 3 + 1);
+            const size_t used = parse_steps(steps.p, steps.n, [&](uint64_t seg, bool fwd) {
+                out.steps.push_back(Handle::make(seg_ids.get(seg), fwd));
+            });
+            if (used != steps.n) throw Error("malformed step list");   // parse.rs:155 assert
+        } catch (const std::exception& e) {
+            out.error = e.what();
+        }
+        return out;
     }
+    void add_parsed_path(const ParsedPath& pp) {                   // parse.rs:151-158
+        if (!pp.error.empty()) throw Error(pp.error);
+        const Span span = HeapGFAStore::add_slice(flat.steps, pp.steps.data(), pp.steps.size());
+        flat.add_path(pp.name.p, pp.name.n, span, pp.overlaps);
+    }
+    void path(const uint8_t* line, size_t n) { add_parsed_path(parse_path(line, n)); }
     void other(const uint8_t* line, size_t n) {   // gfaline.rs:37-49 for H / S / anything else
         if (n < 2 || line[1] != '\t') throw Error("expected marker and tab");
         switch (line[0]) {
@@ -180,8 +202,33 @@ HeapGFAStore Parser::parse_mem(const uint8_t* buf, size_t len) {
         }
         b.other(line, n);
     }
-    for (auto& d : deferred) {   // parse.rs:110-123: in file order
-        if (d.first[0] == 'L') b.link(d.first, d.second); else b.path(d.first, d.second);
+    // parse.rs:110-123: links and paths are added in file order.  The step lists are
+    // tokenised ahead of that by a few worker threads when there is enough text to pay for them.
+    size_t path_bytes = 0, n_path_lines = 0;
+    for (auto& d : deferred)
+        if (d.first[0] == 'P') { path_bytes += d.second; ++n_path_lines; }
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<Builder::ParsedPath> parsed;
+    if (hw > 1 && n_path_lines > 1 && path_bytes > (4u << 20)) {
+        std::vector<size_t> idx;
+        for (size_t i = 0; i < deferred.size(); ++i)
+            if (deferred[i].first[0] == 'P') idx.push_back(i);
+        parsed.resize(idx.size());
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t k; (k = next.fetch_add(1)) < idx.size();)
+                parsed[k] = b.parse_path(deferred[idx[k]].first, deferred[idx[k]].second);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < std::min<size_t>(hw, idx.size()); ++t) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+    }
+    size_t k = 0;
+    for (auto& d : deferred) {
+        if (d.first[0] == 'L') b.link(d.first, d.second);
+        else if (!parsed.empty()) b.add_parsed_path(parsed[k++]);
+        else b.path(d.first, d.second);
     }
     return std::move(b.flat);
 }

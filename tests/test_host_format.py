@@ -237,3 +237,42 @@ def test_reference_c_example_builds_and_runs_unchanged(tmp_path):
     out = subprocess.run(["./example", os.path.join(GOLD, "ref_tiny.gfa")], cwd=tmp_path / "example",
                          capture_output=True, check=True).stdout
     assert out == b"one:\n  + CAAATAAG\n  + AAATTTTCTGGAGTTCTAT\ntwo:\n  + CAAATAAG\n  + AAATTTTCTGGAGTTCTAT\n"
+
+
+def _write_gfa(path, steps, start, end, n_segs, bad_path=None):
+    with open(path, "wb") as f:
+        f.write(b"H\tVN:Z:1.0\n")
+        f.write(("\n".join(f"S\t{i}\tA" for i in range(1, n_segs + 1)) + "\n").encode())
+        for p in range(len(start)):
+            h = steps[start[p]:end[p]]
+            toks = np.char.add(((h >> 1) + 1).astype(str), np.where(h & 1, "-", "+"))
+            body = ",".join(toks.tolist())
+            if p == bad_path:
+                body = body[: len(body) // 2] + ";" + body[len(body) // 2:]
+            f.write(b"P\tp%d\t" % p + body.encode() + b"\t*\n")
+
+
+def test_threaded_step_list_tokenisation_is_exact(tmp_path, fgfa_bin):
+    """Large P lines are tokenised by worker threads (same pools, same order as the serial
+    reference parser, parse.rs:110-123); a malformed line still fails the whole parse."""
+    cfg = synth.Config("big", 20_000, 6, 1_200_000, synth.KIND_WALK, 25, "")
+    steps, s, e = synth.make_graph(cfg)
+    src, out = tmp_path / "big.gfa", tmp_path / "big.flatgfa"
+    _write_gfa(src, steps, s, e, cfg.n_segs)
+    assert src.stat().st_size > (4 << 20)
+    subprocess.run([fgfa_bin, "-I", str(src), "-o", str(out)], check=True)
+    img = out.read_bytes()
+    want = flatgfa_io.build_image(steps, s, e, cfg.n_segs)
+    rc, names, d, u = O.file_depth(img)
+    rc2, names2, d2, u2 = O.file_depth(want.tobytes())
+    assert rc == 0 and rc2 == 0 and (d == d2).all() and (u == u2).all()
+    with pb.FlatGFA.load(str(out)) as g:
+        assert g.path_count == cfg.n_paths
+        for p in (0, 3, 5):
+            assert g.path_name(p) == b"p%d" % p and g.path_step_count(p) == int(e[p] - s[p])
+            for i in (0, 1, int(e[p] - s[p]) - 1):
+                h = int(steps[s[p] + i])
+                assert g.step(p, i) == (h >> 1, not (h & 1))
+    _write_gfa(src, steps, s, e, cfg.n_segs, bad_path=4)
+    with pytest.raises(pb.DepthError):
+        pb.FlatGFA.parse(str(src))
