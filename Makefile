@@ -10,11 +10,15 @@ CSRC      := pollen_b200/csrc
 LIBDIR    := pollen_b200/lib
 OBJDIR    := build/obj
 
-LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/ops_depth.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/capi.o
+LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/ops_depth.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/capi.o
 
 all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools
 
 $(OBJDIR)/depth_device.o: $(CSRC)/depth_device.cu $(CSRC)/depth_kernels.cuh include/fgfa_depth.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJDIR)/tokenize.o: $(CSRC)/tokenize.cu $(CSRC)/tokenize_kernels.cuh include/fgfa_depth.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

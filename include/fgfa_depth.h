@@ -44,7 +44,8 @@ enum {
     FGFA_ERR_CUDA = -6,        /* CUDA runtime failure; see fgfa_last_error() */
     FGFA_ERR_NOMEM = -7,
     FGFA_ERR_NO_DEVICE = -8,   /* no usable CUDA device: the product has no CPU path */
-    FGFA_ERR_TOO_LARGE = -9    /* counts do not fit the format's u32 ids (pool.rs:9-11) */
+    FGFA_ERR_TOO_LARGE = -9,   /* counts do not fit the format's u32 ids (pool.rs:9-11) */
+    FGFA_ERR_PARSE = -10       /* step-list text outside the strict grammar, or an unknown segment name */
 };
 
 /* Static description of an error code. */
@@ -175,6 +176,27 @@ int fgfa_flatgfa_counts(const void* flatgfa_bytes, size_t len, uint64_t* n_segs,
 int fgfa_seg_depth_with_uniq(const void* flatgfa_bytes, size_t len, uint64_t* depth_out,
                              uint64_t* uniq_out);
 int fgfa_seg_depth(const void* flatgfa_bytes, size_t len, uint64_t* depth_out);
+
+/* ---- GPU step-list tokenizer -------------------------------------
+ * The text of GFA path step lists (`1+,23-,4+`) -> Handle words on the device: the GPU form
+ * of `StepsParser` (gfaline.rs:201-263) + `NameMap::get` (namemap.rs:27-33) + `Handle::new`
+ * (flatgfa.rs:192-198), the inner loop of `Parser::add_path` (parse.rs:149-156).
+ * `h_text` is any host buffer (typically the mmapped GFA file); field f is the steps field
+ * of the f-th P line: bytes [field_off[f], field_off[f]+field_len[f]).  create() uploads the
+ * text and counts the steps of every field; parse() resolves names with the reference's
+ * NameMap contents (names 1..sequential_max map to name-1; `other_names[i]` -> `other_ids[i]`)
+ * and writes the steps of all fields back to back (field order) to h_steps_out (may be NULL:
+ * the steps stay on the device, see fgfa_tokenizer_device_steps).  Only the strict grammar
+ * token (',' token)*, token = digit+ ('+'|'-'), is accepted: FGFA_ERR_PARSE means "re-parse
+ * this input with the host parser", which reproduces the reference's quirks and errors. */
+typedef struct fgfa_tokenizer fgfa_tokenizer_t;
+int fgfa_tokenizer_create(fgfa_tokenizer_t** out, const uint8_t* h_text, uint64_t n_bytes,
+                          const uint64_t* field_off, const uint64_t* field_len, uint32_t n_fields);
+int fgfa_tokenizer_spans(const fgfa_tokenizer_t* t, uint32_t* span_start, uint32_t* span_end, uint64_t* n_steps);
+int fgfa_tokenizer_parse(fgfa_tokenizer_t* t, uint64_t sequential_max, const uint64_t* other_names,
+                         const uint32_t* other_ids, uint32_t n_others, uint32_t* h_steps_out);
+const uint32_t* fgfa_tokenizer_device_steps(const fgfa_tokenizer_t* t);
+void fgfa_tokenizer_destroy(fgfa_tokenizer_t* t);
 
 /* Number of CUDA devices visible (0 if none / no driver). */
 int fgfa_device_count(void);

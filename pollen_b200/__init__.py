@@ -19,6 +19,7 @@ from .binding import (  # noqa: F401
     seg_depth_steps,
     seg_depth_with_uniq,
     seg_depth_with_uniq_steps,
+    tokenize_steps,
 )
 
 __all__ = [
@@ -33,4 +34,5 @@ __all__ = [
     "seg_depth_steps",
     "seg_depth_with_uniq",
     "seg_depth_with_uniq_steps",
+    "tokenize_steps",
 ]

@@ -26,6 +26,7 @@ FGFA_ERR_CUDA = -6
 FGFA_ERR_NOMEM = -7
 FGFA_ERR_NO_DEVICE = -8
 FGFA_ERR_TOO_LARGE = -9
+FGFA_ERR_PARSE = -10
 
 
 class DepthError(RuntimeError):
@@ -85,6 +86,11 @@ EXPORTS = {
     "fgfa_depth_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_seg_depth_with_uniq_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fgfa_release_workspace": (None, []),
+    "fgfa_tokenizer_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "fgfa_tokenizer_spans": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "fgfa_tokenizer_parse": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "fgfa_tokenizer_device_steps": (C.c_void_p, [C.c_void_p]),
+    "fgfa_tokenizer_destroy": (None, [C.c_void_p]),
     "fgfa_path_depth_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_path_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_flatgfa_counts": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -159,6 +165,33 @@ def path_depth_steps(steps, span_start, span_end, seg_len, path_ids=None):
         )
     )
     return lengths, weighted, means
+
+
+def tokenize_steps(text: bytes, fields, sequential_max: int, others=None):
+    """GPU step-list tokenizer: ``fields`` is a list of (offset, length) of step-list text inside
+    ``text``; names 1..sequential_max map to name-1, ``others`` is {name: id}.  Returns
+    (steps u32, span_start, span_end); raises DepthError(FGFA_ERR_PARSE) outside the strict grammar."""
+    buf = np.frombuffer(text, dtype=np.uint8)
+    off = np.ascontiguousarray([f[0] for f in fields], dtype=np.uint64)
+    ln = np.ascontiguousarray([f[1] for f in fields], dtype=np.uint64)
+    h = C.c_void_p()
+    _check(lib().fgfa_tokenizer_create(C.byref(h), buf.ctypes.data if buf.size else None, buf.size,
+                                       off.ctypes.data, ln.ctypes.data, len(fields)))
+    try:
+        start = np.empty(len(fields), dtype=np.uint32)
+        end = np.empty(len(fields), dtype=np.uint32)
+        n = C.c_uint64()
+        _check(lib().fgfa_tokenizer_spans(h, start.ctypes.data, end.ctypes.data, C.byref(n)))
+        steps = np.empty(n.value, dtype=np.uint32)
+        others = others or {}
+        names = np.ascontiguousarray(list(others.keys()), dtype=np.uint64)
+        ids = np.ascontiguousarray(list(others.values()), dtype=np.uint32)
+        _check(lib().fgfa_tokenizer_parse(h, sequential_max, names.ctypes.data if names.size else None,
+                                          ids.ctypes.data if ids.size else None, names.size,
+                                          steps.ctypes.data if steps.size else None))
+        return steps, start, end
+    finally:
+        lib().fgfa_tokenizer_destroy(h)
 
 
 def seg_depth_steps(steps, span_start, span_end, n_segs: int) -> np.ndarray:

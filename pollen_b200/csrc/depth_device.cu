@@ -190,6 +190,7 @@ const char* fgfa_strerror(int code) {
         case FGFA_ERR_NOMEM: return "out of memory";
         case FGFA_ERR_NO_DEVICE: return "no CUDA device available (this library has no CPU path)";
         case FGFA_ERR_TOO_LARGE: return "graph too large for the format's 32-bit ids";
+        case FGFA_ERR_PARSE: return "step list outside the strict grammar or unknown segment name";
         default: return "unknown error";
     }
 }

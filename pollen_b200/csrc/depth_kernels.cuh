@@ -15,6 +15,7 @@
 //             (`measure_path`, depth.rs:116-131).
 //   kernel X  (k_uniq_exchange) kernel B fused with the multi-GPU reduce-scatter /
 //             all-gather of depth and uniq over NVLink peer memory.
+// (kernels T1/T2, the step-list tokenizer, live in tokenize_kernels.cuh.)
 //
 // Work decomposition: a *chunk* is up to kChunk consecutive steps of ONE path
 // (a chunk never straddles two paths because the bitmap row depends on the path);

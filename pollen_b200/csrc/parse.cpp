@@ -1,7 +1,10 @@
 #include "parse.hpp"
 
+#include "../../include/fgfa_depth.h"
+
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -184,6 +187,15 @@ struct Builder {
 
 }  // namespace
 
+static bool gpu_paths(Builder& b, const uint8_t* buf, size_t len,
+                      const std::vector<std::pair<const uint8_t*, size_t>>& deferred);
+static bool gpu_paths_hook(Builder& b, const uint8_t* buf, size_t len,
+                           const std::vector<std::pair<const uint8_t*, size_t>>& deferred) {
+    // links must still be added in file order relative to the paths, and a link that fails to
+    // parse must fail the same way on both routes: only take the GPU route when it succeeds whole
+    return gpu_paths(b, buf, len, deferred);
+}
+
 HeapGFAStore Parser::parse_mem(const uint8_t* buf, size_t len) {
     Builder b;
     std::vector<std::pair<const uint8_t*, size_t>> deferred;
@@ -202,6 +214,7 @@ HeapGFAStore Parser::parse_mem(const uint8_t* buf, size_t len) {
         }
         b.other(line, n);
     }
+    if (gpu_paths_hook(b, buf, len, deferred)) return std::move(b.flat);
     // parse.rs:110-123: links and paths are added in file order.  The step lists are
     // tokenised ahead of that by a few worker threads when there is enough text to pay for them.
     size_t path_bytes = 0, n_path_lines = 0;
@@ -231,6 +244,74 @@ HeapGFAStore Parser::parse_mem(const uint8_t* buf, size_t len) {
         else b.path(d.first, d.second);
     }
     return std::move(b.flat);
+}
+
+// GPU route for the step lists: tokenise every P line's steps field with
+// fgfa_tokenizer_* and add the paths with the spans it reports.  Returns false -- leaving the
+// store untouched -- when there is no device, the text is small, or the input is outside the
+// tokenizer's strict grammar; the caller then takes the host route above, which reproduces the
+// reference's quirks and error messages.
+static bool gpu_paths(Builder& b, const uint8_t* buf, size_t len,
+                      const std::vector<std::pair<const uint8_t*, size_t>>& deferred) {
+    const char* env = std::getenv("FGFA_GPU_PARSE");
+    if (env && env[0] == '0') return false;
+    size_t path_bytes = 0;
+    for (auto& d : deferred)
+        if (d.first[0] == 'P') path_bytes += d.second;
+    // a process that has no CUDA context yet pays ~1 s to create one: below ~1 GiB of step-list
+    // text the threaded host route (~0.8 GB/s on 16 cores) wins for a one-shot command
+    const size_t threshold = (env && env[0] == '1') ? 0 : ((size_t)1 << 30);
+    if (path_bytes <= threshold || fgfa_device_count() <= 0) return false;
+    struct Fields { Cursor name; Cursor rest; };
+    std::vector<Fields> lines;
+    std::vector<uint64_t> off, flen;
+    for (auto& d : deferred) {
+        if (d.first[0] != 'P') continue;
+        if (d.second < 2 || d.first[1] != '\t') return false;
+        Cursor c{d.first + 2, d.second - 2};
+        Fields f;
+        f.name = parse_field(c);
+        Cursor steps = parse_field(c);
+        f.rest = c;
+        off.push_back((uint64_t)(steps.p - buf));
+        flen.push_back(steps.n);
+        lines.push_back(f);
+    }
+    fgfa_tokenizer_t* tok = nullptr;
+    if (fgfa_tokenizer_create(&tok, buf, len, off.data(), flen.data(), (uint32_t)off.size()) != FGFA_OK) return false;
+    struct Guard { fgfa_tokenizer_t* t; ~Guard() { fgfa_tokenizer_destroy(t); } } guard{tok};
+    std::vector<uint32_t> ss(off.size()), se(off.size());
+    uint64_t total = 0;
+    if (fgfa_tokenizer_spans(tok, ss.data(), se.data(), &total) != FGFA_OK) return false;
+    const size_t prev = b.flat.steps.size();
+    if (prev + total > 0xFFFFFFFFull) return false;
+    std::vector<uint64_t> names;
+    std::vector<uint32_t> ids;
+    for (auto& kv : b.seg_ids.others()) { names.push_back(kv.first); ids.push_back(kv.second); }
+    std::vector<Handle> steps(total);
+    if (fgfa_tokenizer_parse(tok, b.seg_ids.sequential_max(), names.data(), ids.data(), (uint32_t)names.size(),
+                             reinterpret_cast<uint32_t*>(steps.data())) != FGFA_OK)
+        return false;
+    // overlaps are parsed before anything is committed so that a malformed line leaves the store clean
+    std::vector<std::vector<std::vector<AlignOp>>> overlaps(lines.size());
+    try {
+        for (size_t i = 0; i < lines.size(); ++i) {
+            Cursor c = lines[i].rest;
+            overlaps[i] = parse_maybe_overlap_list(c);
+            if (!c.empty()) return false;
+        }
+    } catch (const std::exception&) {
+        return false;
+    }
+    b.flat.steps.insert(b.flat.steps.end(), steps.begin(), steps.end());
+    size_t k = 0;
+    for (auto& d : deferred) {   // parse.rs:110-123: file order
+        if (d.first[0] == 'L') { b.link(d.first, d.second); continue; }
+        const Span span{HeapGFAStore::id(prev + ss[k]), HeapGFAStore::id(prev + se[k])};
+        b.flat.add_path(lines[k].name.p, lines[k].name.n, span, overlaps[k]);
+        ++k;
+    }
+    return true;
 }
 
 HeapGFAStore Parser::parse_stream(FILE* in) {

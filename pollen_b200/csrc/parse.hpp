@@ -17,6 +17,8 @@ class NameMap {
 public:
     void insert(uint64_t name, uint32_t id);
     uint32_t get(uint64_t name) const;   // throws if unknown (reference: HashMap index panic)
+    uint64_t sequential_max() const { return sequential_max_; }
+    const std::unordered_map<uint64_t, uint32_t>& others() const { return others_; }
 private:
     uint64_t sequential_max_ = 0;
     std::unordered_map<uint64_t, uint32_t> others_;
