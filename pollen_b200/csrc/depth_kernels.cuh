@@ -29,7 +29,10 @@
 namespace fgfa {
 
 constexpr int kThreads = 256;          // threads per CTA in kernel A
-constexpr int kItems = 16;             // steps per thread per chunk
+#ifndef FGFA_ITEMS
+#define FGFA_ITEMS 16
+#endif
+constexpr int kItems = FGFA_ITEMS;     // steps per thread per chunk
 constexpr int kChunk = kThreads * kItems;  // 4096 steps = 16 KiB of the pool
 
 // One unit of work of kernel A: up to kChunk consecutive steps of one path.
@@ -173,7 +176,7 @@ __device__ __forceinline__ void red_shared_or(uint32_t* p, uint32_t v) {
 template <int BLOCKS_PER_SM, int SEEN_MODE, int P2 = kItems>
 __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(StreamParams P) {
     constexpr bool WITH_SEEN = SEEN_MODE != kSeenNone;
-    static_assert(P2 == 16 || P2 == 8 || P2 == 4, "P2 must divide kItems and be a multiple of 4");
+    static_assert(P2 == 32 || P2 == 16 || P2 == 8 || P2 == 4, "P2 must divide kItems and be a multiple of 4");
     extern __shared__ uint4 smem_dyn[];
     uint4 (*s_steps)[kChunk / 4] = reinterpret_cast<uint4 (*)[kChunk / 4]>(smem_dyn);
     uint32_t* const s_bits = reinterpret_cast<uint32_t*>(smem_dyn + 2 * (kChunk / 4));   // [kWinWords]

@@ -152,6 +152,8 @@ int main(int argc, char** argv) {
                100.0 * alg_bytes / (avg * 1e6) / 6540.2);
     };
 
+    const bool only_merged = getenv("UBENCH_ONLY_MERGED") != nullptr;   // skip the experimental kernels
+    if (!only_merged)
     for (int bps : {2, 4, 8}) {
         int grid = sms * bps;
         char nm[96];
@@ -160,6 +162,7 @@ int main(int argc, char** argv) {
         snprintf(nm, sizeof nm, "read-only v4 g=%dxSM", bps);
         time_it(nm, [&] { k_step_stream_direct<kModeReadOnly, 0><<<grid, kThreads>>>(P); }, false);
     }
+    if (!only_merged)
     for (int bps : {4, 8}) {
         int grid = sms * bps;
         char nm[96];
@@ -176,7 +179,7 @@ int main(int argc, char** argv) {
         snprintf(nm, sizeof nm, "depth+seen v4 g=%dxSM", bps);
         time_it(nm, [&] { k_step_stream_direct<kModeDepthAndSeen, 0><<<grid, kThreads>>>(P); }, true);
     }
-    {
+    if (!only_merged) {
         int pgrid = (n_words + kPopThreads - 1) / kPopThreads;
         // populate bitmap, then time popcount (it clears as it goes, so refill each rep)
         auto time_pop = [&](const char* nm, auto&& launch) {
@@ -227,12 +230,15 @@ int main(int argc, char** argv) {
             else k_step_stream_first_touch<8><<<grid, kThreads>>>(P);
         };
         for (int bps : {2, 3, 4, 6, 8}) {
+            if (only_merged) break;
             char nm[96];
             snprintf(nm, sizeof nm, "first-touch A only g=%dxSM", bps);
             time_it(nm, [&] { run_ft(bps); }, true);
         }
+        if (!only_merged) {
         time_it("depth-only half-lanes(seg even) g=8xSM", [&] { k_step_stream_direct<kModeDepthHalfLanes, 1><<<sms * 8, kThreads>>>(P); }, false);
         time_it("depth-only pairs(+2 even tid) g=8xSM", [&] { k_step_stream_direct<kModeDepthPairs, 1><<<sms * 8, kThreads>>>(P); }, false);
+        }
         const size_t smD = stream_smem_bytes(kSeenDirect), smW = stream_smem_bytes(kSeenWindow);
         CK(cudaFuncSetAttribute(k_step_stream_merged<8, kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smW));
         CK(cudaFuncSetAttribute(k_step_stream_merged<2, kSeenDeferred>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -240,8 +246,10 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(k_step_stream_merged<4, kSeenDeferred>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CK(cudaFuncSetAttribute(k_step_stream_merged<5, kSeenDeferred>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CK(cudaFuncSetAttribute(k_step_stream_merged<4, kSeenWindow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smW));
+        if (!only_merged) {
         time_it("merged direct-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenDirect><<<sms * 4, kThreads, smD>>>(S); }, true);
         time_it("merged direct-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenDirect><<<sms * 8, kThreads, smD>>>(S); }, true);
+        }
         const size_t smF = stream_smem_bytes(kSeenDeferred);
         time_it("merged deferred-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenDeferred><<<sms * 4, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR <2> grid 4x", [&] { k_step_stream_merged<2, kSeenDeferred><<<sms * 4, kThreads, smF>>>(S); }, true);
@@ -255,15 +263,19 @@ int main(int argc, char** argv) {
         time_it("merged deferred-OR <5> grid 10x", [&] { k_step_stream_merged<5, kSeenDeferred><<<sms * 10, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR <6> grid 5x", [&] { k_step_stream_merged<6, kSeenDeferred><<<sms * 5, kThreads, smF>>>(S); }, true);
         time_it("merged deferred-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenDeferred><<<sms * 8, kThreads, smF>>>(S); }, true);
+        if (!only_merged) {
         time_it("merged window-OR g=4xSM", [&] { k_step_stream_merged<4, kSeenWindow><<<sms * 4, kThreads, smW>>>(S); }, true);
         time_it("merged window-OR g=8xSM", [&] { k_step_stream_merged<8, kSeenWindow><<<sms * 8, kThreads, smW>>>(S); }, true);
         time_it("merged depth-only g=8xSM", [&] { k_step_stream_merged<8, kSeenNone><<<sms * 8, kThreads, smD>>>(S); }, true);
+        }
+        if (!only_merged) {
         time_it("warp-agg A only g=4xSM", [&] { k_step_stream_warp_agg<4><<<sms * 4, kThreads>>>(P); }, true);
         time_it("warp-agg A only g=6xSM", [&] { k_step_stream_warp_agg<6><<<sms * 6, kThreads>>>(P); }, true);
         time_it("warp-agg A only g=8xSM", [&] { k_step_stream_warp_agg<8><<<sms * 8, kThreads>>>(P); }, true);
         time_it("FT exp1 (no pass3) g=4xSM", [&] { k_step_stream_first_touch<4, 1><<<sms * 4, kThreads>>>(P); }, true);
         time_it("FT exp2 (RED.OR, no pass3) g=4xSM", [&] { k_step_stream_first_touch<4, 2><<<sms * 4, kThreads>>>(P); }, true);
         time_it("FT exp3 (no atomics) g=4xSM", [&] { k_step_stream_first_touch<4, 3><<<sms * 4, kThreads>>>(P); }, true);
+        }
         const bool use_wagg = getenv("UBENCH_WAGG") != nullptr;
         const bool use_merged = getenv("UBENCH_MERGED") != nullptr;
         if (use_merged) Q2.depth = nullptr;
