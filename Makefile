@@ -10,7 +10,7 @@ CSRC      := pollen_b200/csrc
 LIBDIR    := pollen_b200/lib
 OBJDIR    := build/obj
 
-LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/ops_depth.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/capi.o
+LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(OBJDIR)/ops_depth.o $(OBJDIR)/ops_window_depth.o $(OBJDIR)/flatbed.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/capi.o
 
 all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools
 
@@ -19,6 +19,10 @@ $(OBJDIR)/depth_device.o: $(CSRC)/depth_device.cu $(CSRC)/depth_kernels.cuh incl
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(OBJDIR)/tokenize.o: $(CSRC)/tokenize.cu $(CSRC)/tokenize_kernels.cuh include/fgfa_depth.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJDIR)/interval_device.o: $(CSRC)/interval_device.cu $(CSRC)/interval_kernels.cuh include/fgfa_depth.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

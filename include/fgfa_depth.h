@@ -163,6 +163,53 @@ int fgfa_path_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint3
                           uint32_t n_segs, const uint32_t* path_ids, uint32_t n_query,
                           uint64_t* length_out, uint64_t* weighted_out, double* mean_out);
 
+/* ---- interval / window depth along one path ------------------------
+ * GPU form of flatgfa/src/ops/window_depth.rs: `path_length` (:69-77), `weighted_depths`
+ * (:84-103), `assign_depths` (:118-153), `interval_depth` (:176-180), `window_depth` (:183-197)
+ * and `bed_depth` (:203-211).  Results are f64 and bit-identical to the reference's: every
+ * interval is summed in step order with the same operation sequence.
+ *
+ * Device level.  `d_path_steps` = the first Handle of the ONE path the intervals lie on
+ * (any 4-byte-aligned device address), `n_path_steps` its step count; `d_depth` = node
+ * depth over all paths (seg_depth, window_depth.rs:177) as u32; `d_seg_len` = Segment::len
+ * per segment.  Scratch: fgfa_interval_scratch_bytes(n_path_steps, n_intervals) bytes.
+ * Calls only enqueue work on `cuda_stream`; fgfa_interval_status() synchronises and reports
+ * a step that named a segment >= n_segs (FGFA_ERR_SEG_OOB). */
+size_t fgfa_interval_scratch_bytes(uint64_t n_path_steps, uint64_t n_intervals);
+/* W1: d_seg_end[j] = end offset in base pairs of step j (inclusive prefix sum of the
+ * segment lengths); d_seg_end[n-1] is `path_length`.  d_seg_end: n_path_steps u64. */
+int fgfa_path_offsets_device(const uint32_t* d_path_steps, uint32_t n_path_steps,
+                             const uint32_t* d_seg_len, uint32_t n_segs, uint64_t* d_seg_end,
+                             void* d_scratch, size_t scratch_bytes, void* cuda_stream);
+/* `Windows` (window_depth.rs:20-52): [start + w*size, min(start + (w+1)*size, end)). */
+int fgfa_make_windows_device(uint64_t start, uint64_t end, uint64_t size, uint64_t n_windows,
+                             uint64_t* d_win_start, uint64_t* d_win_end, void* cuda_stream);
+/* W2 + W3: `assign_depths`.  d_out: n_intervals f64. */
+int fgfa_interval_depth_device(const uint32_t* d_path_steps, uint32_t n_path_steps,
+                               const uint32_t* d_depth, const uint32_t* d_seg_len, uint32_t n_segs,
+                               const uint64_t* d_seg_end, const uint64_t* d_win_start,
+                               const uint64_t* d_win_end, uint64_t n_intervals, double* d_out,
+                               void* d_scratch, size_t scratch_bytes, void* cuda_stream);
+int fgfa_interval_status(const void* d_scratch, void* cuda_stream);
+
+/* Host level (uploads, runs, downloads; synchronous).  Node depth is taken over ALL paths
+ * of the graph, the intervals lie along path `path` (a path pool index).
+ * bed_depth / interval_depth (window_depth.rs:176-180, :203-211): caller-allocated
+ * depth_out with n_intervals entries. */
+int fgfa_interval_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint32_t* h_span_start,
+                              const uint32_t* h_span_end, uint32_t n_paths, const uint32_t* h_seg_len,
+                              uint32_t n_segs, uint32_t path, const uint64_t* h_win_start,
+                              const uint64_t* h_win_end, uint64_t n_intervals, double* depth_out);
+/* window_depth (window_depth.rs:183-197): equally sized windows over the whole path.
+ * *depth_out is allocated by the library (release with fgfa_free) and holds *n_windows_out
+ * values; window w is [w*window_size, min((w+1)*window_size, *path_length_out)).
+ * window_size == 0 is FGFA_ERR_INVALID_ARG (the reference loops forever). */
+int fgfa_window_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint32_t* h_span_start,
+                            const uint32_t* h_span_end, uint32_t n_paths, const uint32_t* h_seg_len,
+                            uint32_t n_segs, uint32_t path, uint64_t window_size, double** depth_out,
+                            uint64_t* n_windows_out, uint64_t* path_length_out);
+void fgfa_free(void* p);
+
 /* The host-buffer entry points keep their device/pinned staging and the last plan in a
  * process-wide workspace between calls; this frees it (it is re-created on demand).
  * Setting FGFA_WORKSPACE=0 in the environment frees it after every call instead. */

@@ -215,3 +215,136 @@ int oracle_format_float(double x, int digits, char* out, size_t cap) {
     while (n > 0 && out[n - 1] == '.') out[--n] = 0;
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Interval ("window") depth, SURVEY §8f-3: flatgfa/src/ops/window_depth.rs and flatbed.rs.
+ * PARITY UNPINNED for these functions: the reference holds no runnable golden for them
+ * (the table in flatgfa-sh/README.md:282-294 needs note5.gfa, fetched from odgi at test
+ * time, plus bedtools).  tests/ cross-check this restatement against an independent
+ * pure-Python restatement written from the same Rust source, and reproduce the README's
+ * table on a hand-made graph with the same shape (every segment of the path at depth 2).
+ * ------------------------------------------------------------------------------------------ */
+
+/* window_depth.rs:61-63 Windows::len = (end - start).div_ceil(size). */
+uint64_t oracle_window_count(uint64_t start, uint64_t end, uint64_t size) {
+    uint64_t span = end - start;
+    return span / size + (span % size ? 1 : 0);
+}
+
+/* window_depth.rs:41-52 Windows::emit_bed: the (start, end) pairs of the windows. */
+void oracle_make_windows(uint64_t start, uint64_t end, uint64_t size, uint64_t* win_start, uint64_t* win_end) {
+    uint64_t pos = start, w = 0;
+    while (pos < end) {                                /* :46 */
+        uint64_t stop = pos + size < end ? pos + size : end;   /* :47 */
+        win_start[w] = pos;
+        win_end[w] = stop;
+        ++w;
+        pos = stop;                                    /* :49 */
+    }
+}
+
+/* window_depth.rs:69-77 path_length. */
+uint64_t oracle_path_length(const uint32_t* steps, const uint32_t* spans, uint32_t path, const uint32_t* seg_len) {
+    uint64_t total = 0;
+    for (uint32_t i = spans[2 * path]; i < spans[2 * path + 1]; ++i) total += seg_len[handle_segment(steps[i])];
+    return total;
+}
+
+/*
+ * window_depth.rs:176-180 interval_depth = seg_depth over ALL paths (:177), weighted_depths
+ * along `path` (:84-103) fed to assign_depths (:118-153).  The loop below is the reference's:
+ * one cursor over the intervals, advanced while the steps stream by.  All f64 operations are
+ * the reference's, in its order; build with -ffp-contract=off.
+ */
+int oracle_interval_depth(const uint32_t* steps, uint64_t n_steps, const uint32_t* spans, uint32_t n_paths,
+                          const uint32_t* seg_len, uint32_t n_segs, uint32_t path, const uint64_t* win_start,
+                          const uint64_t* win_end, uint64_t n_win, double* out) {
+    if (path >= n_paths) return -1;
+    uint64_t* depth = (uint64_t*)malloc((size_t)(n_segs ? n_segs : 1) * sizeof(uint64_t));
+    if (!depth) return -2;
+    int rc = oracle_seg_depth(steps, n_steps, spans, n_paths, n_segs, depth);   /* :177 */
+    if (rc) { free(depth); return rc; }
+    for (uint64_t w = 0; w < n_win; ++w) out[w] = 0.0;          /* :119 */
+    uint64_t cur = 0;                                           /* :122 */
+    uint64_t pos = 0;                                           /* :89 */
+    for (uint32_t i = spans[2 * path]; i < spans[2 * path + 1]; ++i) {   /* :123, :90 */
+        uint32_t seg = handle_segment(steps[i]);
+        uint64_t len = seg_len[seg];
+        uint64_t r0 = pos, r1 = pos + len;                      /* :92-94 */
+        pos = r1;
+        double seg_depth = (double)(depth[seg] * len);          /* :95, :97 */
+        while (cur < n_win) {                                   /* :125 */
+            uint64_t w0 = win_start[cur], w1 = win_end[cur];    /* :126-127 */
+            uint64_t a = w0 > r0 ? w0 : r0;                     /* :128, overlap :110-112 */
+            uint64_t b = w1 < r1 ? w1 : r1;
+            if (b > a) {                                        /* :131 */
+                double amt = (double)(b - a) / (double)(r1 - r0);          /* :133 */
+                out[cur] += (seg_depth * amt) / (double)(w1 - w0);         /* :134-135 */
+            }
+            if (w1 > r1) break;                                 /* :140-142 */
+            ++cur;                                              /* :145 */
+        }
+    }
+    free(depth);
+    return 0;
+}
+
+/*
+ * flatbed.rs:126-152 BEDParser::parse_mem + parse_line.  Lines come from MemchrSplit
+ * (memfile.rs:51-63: an unterminated last line is dropped); `#` lines are skipped;
+ * name = up to the first tab (gfaline.rs:129-142); start = leading digits of the rest
+ * (atoi FromRadix10, wrapping); one byte skipped; end likewise.  Output: per entry the name's
+ * (offset, length) in `buf` and start/end.  Returns the number of entries, -1 where the
+ * reference panics, -3 if `cap` is too small.
+ */
+static size_t oracle_radix10(const uint8_t* s, size_t n, uint64_t* v) {
+    size_t i = 0;
+    *v = 0;
+    while (i < n && s[i] >= '0' && s[i] <= '9') { *v = *v * 10 + (uint64_t)(s[i] - '0'); ++i; }
+    return i;
+}
+int64_t oracle_parse_bed(const uint8_t* buf, uint64_t len, uint64_t* name_off, uint64_t* name_len,
+                         uint64_t* start, uint64_t* end, uint64_t cap) {
+    uint64_t pos = 0, n = 0;
+    while (pos < len) {
+        const uint8_t* nl = (const uint8_t*)memchr(buf + pos, '\n', len - pos);
+        if (!nl) break;
+        const uint8_t* line = buf + pos;
+        size_t ll = (size_t)(nl - line);
+        pos = (uint64_t)(nl - buf) + 1;
+        if (ll && line[0] == '#') continue;                     /* :143-145 */
+        const uint8_t* tab = (const uint8_t*)memchr(line, '\t', ll);
+        size_t nm = tab ? (size_t)(tab - line) : ll;
+        const uint8_t* rest = tab ? tab + 1 : line + ll;
+        size_t rl = tab ? ll - nm - 1 : 0;
+        uint64_t s, e;
+        size_t used = oracle_radix10(rest, rl, &s);             /* :148 */
+        if (!used) return -1;
+        rest += used; rl -= used;
+        if (rl == 0) return -1;                                 /* :149 `&rest[1..]` */
+        used = oracle_radix10(rest + 1, rl - 1, &e);
+        if (!used) return -1;
+        if (n >= cap) return -3;
+        name_off[n] = (uint64_t)(line - buf); name_len[n] = nm; start[n] = s; end[n] = e;
+        ++n;
+    }
+    return (int64_t)n;
+}
+
+/* window_depth.rs:163-174 IntervalDepth::emit: "{name}\t{start}\t{end}\t{format_float(depth, 4)}\n".
+ * Names are (pointer into `names`, length) pairs.  Returns bytes written or -1. */
+int64_t oracle_emit_interval_depth(const uint8_t* names, const uint64_t* name_off, const uint64_t* name_len,
+                                   const uint64_t* start, const uint64_t* end, const double* depth, uint64_t n,
+                                   char* buf, uint64_t cap) {
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        char num[400];
+        if (oracle_format_float(depth[i], 4, num, sizeof num) < 0) return -1;
+        if (cap - w < name_len[i] + 64 + strlen(num)) return -1;
+        memcpy(buf + w, names + name_off[i], name_len[i]);
+        w += name_len[i];
+        w += (uint64_t)snprintf(buf + w, cap - w, "\t%llu\t%llu\t%s\n", (unsigned long long)start[i],
+                                (unsigned long long)end[i], num);
+    }
+    return (int64_t)w;
+}

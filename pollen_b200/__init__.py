@@ -10,9 +10,11 @@ the built library or without a CUDA device raises.
 from .binding import (  # noqa: F401
     DepthError,
     DepthPlan,
+    FlatBED,
     FlatGFA,
     SegDepth,
     device_count,
+    interval_depth_steps,
     lib,
     path_depth_steps,
     seg_depth,
@@ -20,14 +22,17 @@ from .binding import (  # noqa: F401
     seg_depth_with_uniq,
     seg_depth_with_uniq_steps,
     tokenize_steps,
+    window_depth_steps,
 )
 
 __all__ = [
     "DepthError",
     "DepthPlan",
+    "FlatBED",
     "FlatGFA",
     "SegDepth",
     "device_count",
+    "interval_depth_steps",
     "lib",
     "path_depth_steps",
     "seg_depth",
@@ -35,4 +40,5 @@ __all__ = [
     "seg_depth_with_uniq",
     "seg_depth_with_uniq_steps",
     "tokenize_steps",
+    "window_depth_steps",
 ]

@@ -64,6 +64,14 @@ EXPORTS = {
     "flatgfa_path_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "flatgfa_format_path_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "flatgfa_dump": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "flatbed_parse_mem": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+    "flatbed_make_windows": (C.c_void_p, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "flatbed_free": (None, [C.c_void_p]),
+    "flatbed_entry_count": (C.c_uint64, [C.c_void_p]),
+    "flatbed_get_entry": (C.c_bool, [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "flatgfa_interval_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "flatgfa_window_depth": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "flatgfa_bed_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "flatgfa_last_error": (C.c_char_p, []),
     # include/fgfa_depth.h
     "fgfa_strerror": (C.c_char_p, [C.c_int]),
@@ -93,6 +101,14 @@ EXPORTS = {
     "fgfa_tokenizer_destroy": (None, [C.c_void_p]),
     "fgfa_path_depth_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_path_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_interval_scratch_bytes": (C.c_size_t, [C.c_uint64, C.c_uint64]),
+    "fgfa_path_offsets_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "fgfa_make_windows_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_interval_depth_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "fgfa_interval_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fgfa_interval_depth_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "fgfa_window_depth_steps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fgfa_free": (None, [C.c_void_p]),
     "fgfa_flatgfa_counts": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fgfa_seg_depth_with_uniq": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "fgfa_seg_depth": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -167,6 +183,42 @@ def path_depth_steps(steps, span_start, span_end, seg_len, path_ids=None):
     return lengths, weighted, means
 
 
+def interval_depth_steps(steps, span_start, span_end, seg_len, path: int, win_start, win_end):
+    """interval_depth / bed_depth (window_depth.rs:176-180, 203-211) over raw host arrays: mean
+    depth (f64, bit-identical to the reference) of each [win_start, win_end) along path ``path``."""
+    steps, span_start, span_end, seg_len = _u32(steps), _u32(span_start), _u32(span_end), _u32(seg_len)
+    ws = np.ascontiguousarray(win_start, dtype=np.uint64)
+    we = np.ascontiguousarray(win_end, dtype=np.uint64)
+    out = np.empty(ws.size, dtype=np.float64)
+    _check(
+        lib().fgfa_interval_depth_steps(
+            steps.ctypes.data, steps.size, span_start.ctypes.data, span_end.ctypes.data, span_start.size,
+            seg_len.ctypes.data, seg_len.size, path, ws.ctypes.data, we.ctypes.data, ws.size, out.ctypes.data,
+        )
+    )
+    return out
+
+
+def window_depth_steps(steps, span_start, span_end, seg_len, path: int, window_size: int):
+    """window_depth (window_depth.rs:183-197) over raw host arrays.  Returns (win_start u64,
+    win_end u64, depths f64, path_length)."""
+    steps, span_start, span_end, seg_len = _u32(steps), _u32(span_start), _u32(span_end), _u32(seg_len)
+    out, m, total = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    _check(
+        lib().fgfa_window_depth_steps(
+            steps.ctypes.data, steps.size, span_start.ctypes.data, span_end.ctypes.data, span_start.size,
+            seg_len.ctypes.data, seg_len.size, path, window_size, C.byref(out), C.byref(m), C.byref(total),
+        )
+    )
+    try:
+        depths = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(m.value,)).copy() if m.value else np.empty(0)
+    finally:
+        lib().fgfa_free(out)
+    ws = np.arange(m.value, dtype=np.uint64) * np.uint64(window_size)
+    we = np.minimum(ws + np.uint64(window_size), np.uint64(total.value))
+    return ws, we, depths, total.value
+
+
 def tokenize_steps(text: bytes, fields, sequential_max: int, others=None):
     """GPU step-list tokenizer: ``fields`` is a list of (offset, length) of step-list text inside
     ``text``; names 1..sequential_max map to name-1, ``others`` is {name: id}.  Returns
@@ -197,6 +249,49 @@ def tokenize_steps(text: bytes, fields, sequential_max: int, others=None):
 def seg_depth_steps(steps, span_start, span_end, n_segs: int) -> np.ndarray:
     """seg_depth (depth.rs:45-56) over raw host arrays."""
     return seg_depth_with_uniq_steps(steps, span_start, span_end, n_segs, want_uniq=False)[0]
+
+
+class FlatBED:
+    """A list of named intervals (``flatbed_t``; flatbed.rs:19-33): a parsed BED file or the
+    equally sized windows of ``Windows`` (window_depth.rs:20-58)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise DepthError(FGFA_ERR_INVALID_ARG, lib().flatgfa_last_error().decode())
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def parse(cls, bed_text: bytes) -> "FlatBED":  # BEDParser::parse_mem, flatbed.rs:126-131
+        buf = C.create_string_buffer(bed_text, len(bed_text))
+        return cls(lib().flatbed_parse_mem(C.cast(buf, C.c_void_p), len(bed_text)))
+
+    @classmethod
+    def windows(cls, name: bytes, start: int, end: int, size: int) -> "FlatBED":  # Windows::as_bed
+        buf = C.create_string_buffer(name, len(name))
+        return cls(lib().flatbed_make_windows(C.cast(buf, C.c_void_p), len(name), start, end, size))
+
+    def close(self) -> None:
+        if self._h:
+            lib().flatbed_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(lib().flatbed_entry_count(self._h))
+
+    def entries(self):
+        """[(name bytes, start, end)] in file order."""
+        out = []
+        s, a, b = _String(), C.c_uint64(), C.c_uint64()
+        for i in range(len(self)):
+            assert lib().flatbed_get_entry(self._h, i, C.byref(s), C.byref(a), C.byref(b))
+            out.append((C.string_at(s.data, s.len) if s.len else b"", a.value, b.value))
+        return out
 
 
 class FlatGFA:
@@ -287,6 +382,31 @@ class FlatGFA:
         out, n = C.c_void_p(), C.c_size_t()
         _check(lib().flatgfa_format_path_depth(self._h, None if ids is None else ids.ctypes.data, lengths.size,
                                                lengths.ctypes.data, means.ctypes.data, C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            C.CDLL(None).free(out)
+
+    def interval_depth(self, bed: "FlatBED") -> np.ndarray:
+        """``ops::window_depth::bed_depth`` (window_depth.rs:203-211): one f64 per entry."""
+        out = np.empty(len(bed), dtype=np.float64)
+        _check(lib().flatgfa_interval_depth(self._h, bed._h, out.ctypes.data))
+        return out
+
+    def window_depth(self, path_name: str, window_size: int) -> bytes:
+        """``fgfa window-depth PATH SIZE`` (cmds.rs:477-496): the IntervalDepth table."""
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().flatgfa_window_depth(self._h, path_name.encode(), window_size, C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            C.CDLL(None).free(out)
+
+    def bed_depth(self, bed_text: bytes) -> bytes:
+        """``fgfa depth -b BED`` (cmds.rs:246-255): the IntervalDepth table for a BED file's text."""
+        out, n = C.c_void_p(), C.c_size_t()
+        buf = C.create_string_buffer(bed_text, len(bed_text))
+        _check(lib().flatgfa_bed_depth(self._h, C.cast(buf, C.c_void_p), len(bed_text), C.byref(out), C.byref(n)))
         try:
             return C.string_at(out, n.value)
         finally:

@@ -10,6 +10,7 @@
 #include "../../include/flatgfa.h"
 #include "file.hpp"
 #include "ops_depth.hpp"
+#include "ops_window_depth.hpp"
 #include "parse.hpp"
 
 // lib.rs:16: the opaque store behind flatgfa_t.  Either a parsed heap store or a
@@ -18,6 +19,10 @@ struct CStore {
     flatgfa::HeapGFAStore heap;
     std::unique_ptr<flatgfa::MappedFile> map;
     flatgfa::FlatGFA gfa;
+};
+
+struct flatbed {
+    flatgfa::HeapBEDStore store;
 };
 
 namespace {
@@ -191,6 +196,103 @@ int flatgfa_format_path_depth(flatgfa_t gfa, const uint32_t* path_ids, uint32_t 
     *out = buf;
     *out_len = s.size();
     return FGFA_OK;
+}
+
+namespace {
+int text_out(const std::string& s, char** out, size_t* out_len) {
+    char* buf = static_cast<char*>(std::malloc(s.size() + 1));
+    if (!buf) return FGFA_ERR_NOMEM;
+    std::memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+    *out = buf;
+    *out_len = s.size();
+    return FGFA_OK;
+}
+int code_of(const std::exception& e) {
+    g_err = e.what();
+    if (std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "no usable CUDA device")) return FGFA_ERR_NO_DEVICE;
+    return FGFA_ERR_INVALID_ARG;
+}
+}  // namespace
+
+flatbed_t flatbed_parse_mem(const uint8_t* bed_text, size_t bed_len) {
+    if (bed_len && !bed_text) { g_err = "null text"; return nullptr; }
+    try {
+        std::unique_ptr<flatbed> b(new flatbed);
+        b->store = flatgfa::BEDParser::parse_mem(bed_text, bed_len);
+        return b.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+flatbed_t flatbed_make_windows(const uint8_t* name, size_t name_len, uint64_t start, uint64_t end, uint64_t size) {
+    if (size == 0 || (name_len && !name)) { g_err = "window size must be positive"; return nullptr; }
+    try {
+        std::unique_ptr<flatbed> b(new flatbed);
+        b->store = flatgfa::ops::window_depth::Windows{{name, name_len}, start, end, size}.as_bed();
+        return b.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+void flatbed_free(flatbed_t bed) { delete bed; }
+
+uint64_t flatbed_entry_count(flatbed_t bed) { return bed ? bed->store.entries.size() : 0; }
+
+bool flatbed_get_entry(flatbed_t bed, uint64_t i, flatgfa_string_t* name, uint64_t* start, uint64_t* end) {
+    if (!bed || i >= bed->store.entries.size()) return false;
+    const flatgfa::BEDEntry& e = bed->store.entries[i];
+    if (name) {
+        name->data = bed->store.name_data.data() + e.name.start;
+        name->len = (int)(e.name.end - e.name.start);
+    }
+    if (start) *start = e.start;
+    if (end) *end = e.end;
+    return true;
+}
+
+int flatgfa_interval_depth(flatgfa_t gfa, flatbed_t bed, double* depths) {
+    if (!gfa || !bed || (!depths && !bed->store.entries.empty())) return FGFA_ERR_INVALID_ARG;
+    try {
+        auto d = flatgfa::ops::window_depth::bed_depth(gfa->gfa, bed->store.view());
+        std::memcpy(depths, d.data(), d.size() * sizeof(double));
+        return FGFA_OK;
+    } catch (const std::exception& e) {
+        return code_of(e);
+    }
+}
+
+int flatgfa_window_depth(flatgfa_t gfa, const char* path_name, uint64_t window_size, char** out, size_t* out_len) {
+    if (!gfa || !path_name || !out || !out_len) return FGFA_ERR_INVALID_ARG;
+    try {
+        const int64_t path = gfa->gfa.find_path(reinterpret_cast<const uint8_t*>(path_name), std::strlen(path_name));
+        if (path < 0) { g_err = "path not found"; return FGFA_ERR_INVALID_ARG; }              // cmds.rs:489
+        auto wd = flatgfa::ops::window_depth::window_depth(gfa->gfa, (uint32_t)path, window_size);
+        flatgfa::ops::window_depth::IntervalDepth t{wd.first.view(), std::move(wd.second)};
+        std::string s;
+        t.emit(s);
+        return text_out(s, out, out_len);
+    } catch (const std::exception& e) {
+        return code_of(e);
+    }
+}
+
+int flatgfa_bed_depth(flatgfa_t gfa, const uint8_t* bed_text, size_t bed_len, char** out, size_t* out_len) {
+    if (!gfa || (bed_len && !bed_text) || !out || !out_len) return FGFA_ERR_INVALID_ARG;
+    try {
+        const flatgfa::HeapBEDStore store = flatgfa::BEDParser::parse_mem(bed_text, bed_len);   // cmds.rs:248-249
+        auto depths = flatgfa::ops::window_depth::bed_depth(gfa->gfa, store.view());            // cmds.rs:250
+        flatgfa::ops::window_depth::IntervalDepth t{store.view(), std::move(depths)};
+        std::string s;
+        t.emit(s);
+        return text_out(s, out, out_len);
+    } catch (const std::exception& e) {
+        return code_of(e);
+    }
 }
 
 int flatgfa_dump(flatgfa_t gfa, const char* filename) {

@@ -5,10 +5,13 @@
 // dispatch, main.rs:190-213 `dump`):
 //   fgfa [-i FLATGFA | -I GFA | < GFA] depth -d          node-depth table on stdout
 //   fgfa [-i FLATGFA | -I GFA | < GFA] depth [-r PATH]   path-depth table (cmds.rs:256-283)
+//   fgfa [-i FLATGFA | -I GFA | < GFA] depth -b BED      interval depth table (cmds.rs:246-255)
+//   fgfa [-i FLATGFA | -I GFA | < GFA] window-depth PATH SIZE   (cmds.rs:477-496)
 //   fgfa [-i FLATGFA | -I GFA | < GFA] -o OUT.flatgfa    convert to the binary format
-// The other thirteen subcommands of the reference are outside this repository's scope
+// The other subcommands of the reference are outside this repository's scope
 // and are rejected with an error.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -16,6 +19,7 @@
 
 #include "file.hpp"
 #include "ops_depth.hpp"
+#include "ops_window_depth.hpp"
 #include "parse.hpp"
 
 namespace {
@@ -29,6 +33,8 @@ struct Args {
     bool seg_depth = false;                             // -d / --graph-depth-table
     std::vector<std::string> paths;                     // -r
     std::string bed;                                    // -b / --bed-input
+    // window-depth (cmds.rs:477-486)
+    std::vector<std::string> positional;
 };
 
 int usage(const char* msg) {
@@ -38,7 +44,10 @@ int usage(const char* msg) {
                  "[-p <prealloc-factor>] [<command>] [<args>]\n\n"
                  "Convert between GFA text and FlatGFA binary formats.\n\n"
                  "Commands:\n  depth             compute depth: the number of times paths cross a node\n"
-                 "                    -d, --graph-depth-table  compute node depth instead of path depth\n");
+                 "                    -d, --graph-depth-table  compute node depth instead of path depth\n"
+                 "                    -r <path>                in path mode, show only the named path\n"
+                 "                    -b, --bed-input <bed>    show depth for intervals from a BED file\n"
+                 "  window-depth      find the depth of windows along a path: window-depth <path> <window>\n");
     return 1;
 }
 
@@ -73,6 +82,9 @@ int main(int argc, char** argv) {
             else if (t == "-b" || t == "--bed-input") { if (!take(i, argc, argv, a.bed)) return usage("No value provided for option '-b'."); }
             else return usage(("Unrecognized argument: " + t).c_str());
         }
+    } else if (a.command == "window-depth") {
+        for (; i < argc; ++i) a.positional.push_back(argv[i]);
+        if (a.positional.size() != 2) return usage("window-depth takes two positional arguments: <path> <window>");
     } else if (!a.command.empty()) {
         std::fprintf(stderr, "fgfa: subcommand '%s' is outside the scope of this build (node depth only)\n",
                      a.command.c_str());
@@ -101,9 +113,12 @@ int main(int argc, char** argv) {
         }
 
         if (a.command == "depth") {                                           // main.rs:136-138
-            if (!a.seg_depth && !a.bed.empty()) {
-                std::fprintf(stderr, "fgfa depth: BED interval mode (-b) is outside the scope of this build\n");
-                return 1;
+            if (!a.seg_depth && !a.bed.empty()) {                             // cmds.rs:246-255: interval depth table
+                flatgfa::MappedFile file(a.bed);
+                const flatgfa::HeapBEDStore bed = flatgfa::BEDParser::parse_mem(file.data(), file.size());
+                auto depths = flatgfa::ops::window_depth::bed_depth(gfa, bed.view());
+                flatgfa::ops::window_depth::IntervalDepth{bed.view(), std::move(depths)}.print();
+                return 0;
             }
             if (!a.seg_depth) {                                               // cmds.rs:256-283: path depth table
                 std::vector<uint32_t> ids;
@@ -126,6 +141,18 @@ int main(int argc, char** argv) {
             }
             auto du = flatgfa::ops::depth::seg_depth_with_uniq(gfa);          // cmds.rs:239
             flatgfa::ops::depth::SegDepth{gfa, std::move(du.first), std::move(du.second)}.print();  // cmds.rs:240-245
+            return 0;
+        }
+
+        if (a.command == "window-depth") {                                    // main.rs:178-180, cmds.rs:488-496
+            const std::string& name = a.positional[0];
+            char* endp = nullptr;
+            const unsigned long long window = std::strtoull(a.positional[1].c_str(), &endp, 10);
+            if (a.positional[1].empty() || *endp) return usage("window-depth: <window> must be a number");
+            const int64_t path = gfa.find_path(reinterpret_cast<const uint8_t*>(name.data()), name.size());
+            if (path < 0) throw flatgfa::Error("path not found");
+            auto wd = flatgfa::ops::window_depth::window_depth(gfa, (uint32_t)path, window);
+            flatgfa::ops::window_depth::IntervalDepth{wd.first.view(), std::move(wd.second)}.print();
             return 0;
         }
 

@@ -9,6 +9,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -117,6 +118,14 @@ struct FlatGFA {
     Pool<uint8_t> get_seq(const Segment& seg) const { return seq_data.slice(seg.seq); }       // flatgfa.rs:354-356
     Pool<uint8_t> get_path_name(const Path& p) const { return name_data.slice(p.name); }       // flatgfa.rs:381-383
     Pool<Handle> get_path_steps(const Path& p) const { return steps.slice(p.steps); }          // flatgfa.rs:385-387
+    // flatgfa.rs:387-389 + pool.rs:305-307: index of the first path with this name, or -1.
+    int64_t find_path(const uint8_t* name, size_t n) const {
+        for (size_t p = 0; p < paths.len(); ++p) {
+            const Pool<uint8_t> nm = get_path_name(paths.data[p]);
+            if (nm.len() == n && (n == 0 || std::memcmp(nm.data, name, n) == 0)) return (int64_t)p;
+        }
+        return -1;
+    }
 };
 
 // flatgfa.rs:426-552: the growable in-memory store (HeapGFAStore) the parser fills.

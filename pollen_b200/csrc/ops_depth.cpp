@@ -27,7 +27,8 @@ struct Workspace {
     uint32_t* steps = nullptr;  size_t steps_cap = 0;     // elements
     uint32_t* out = nullptr;    size_t out_cap = 0;       // elements ([depth | uniq])
     uint32_t* h_out = nullptr;  size_t h_out_cap = 0;     // pinned, elements
-    void* aux = nullptr;        size_t aux_cap = 0;       // bytes (path-depth scratch)
+    void* aux = nullptr;        size_t aux_cap = 0;       // bytes (path-depth scratch / step offsets)
+    void* aux2 = nullptr;       size_t aux2_cap = 0;      // bytes (interval depth: intervals, scratch, results)
     cudaStream_t copy = nullptr, compute = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     fgfa_depth_plan_t* plan = nullptr;
@@ -41,6 +42,7 @@ struct Workspace {
         if (h_out) cudaFreeHost(h_out);
         h_out = nullptr; h_out_cap = 0;
         cudaFree(aux); aux = nullptr; aux_cap = 0;
+        cudaFree(aux2); aux2 = nullptr; aux2_cap = 0;
         for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
         if (copy) cudaStreamDestroy(copy);
         if (compute) cudaStreamDestroy(compute);
@@ -303,6 +305,127 @@ int fgfa_seg_depth_with_uniq(const void* bytes, size_t len, uint64_t* depth_out,
 int fgfa_seg_depth(const void* bytes, size_t len, uint64_t* depth_out) {
     return depth_of_image(bytes, len, depth_out, nullptr);
 }
+
+}  // extern "C"
+
+namespace {
+size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+// Shared body of fgfa_interval_depth_steps (h_win_* given) and fgfa_window_depth_steps
+// (window_size given): window_depth.rs:176-197.
+int interval_depth_host(const uint32_t* h_steps, uint64_t n_steps, const uint32_t* h_span_start,
+                        const uint32_t* h_span_end, uint32_t n_paths, const uint32_t* h_seg_len,
+                        uint32_t n_segs, uint32_t path, const uint64_t* h_win_start, const uint64_t* h_win_end,
+                        uint64_t n_intervals, uint64_t window_size, double* depth_out, double** depth_alloc,
+                        uint64_t* n_windows_out, uint64_t* path_length_out) {
+    const bool uniform = depth_alloc != nullptr;
+    if ((n_steps && !h_steps) || !h_span_start || !h_span_end || (n_segs && !h_seg_len) || path >= n_paths)
+        return FGFA_ERR_INVALID_ARG;
+    if (uniform ? window_size == 0 : (n_intervals && (!h_win_start || !h_win_end || !depth_out)))
+        return FGFA_ERR_INVALID_ARG;
+    if (fgfa_device_count() <= 0) return FGFA_ERR_NO_DEVICE;
+    Workspace& W = g_ws;
+    std::lock_guard<std::mutex> lock(W.mu);
+    const char* env = std::getenv("FGFA_WORKSPACE");
+    const bool keep = !(env && env[0] == '0');
+    struct Releaser { Workspace& w; bool on; ~Releaser() { if (on) w.release(); } } releaser{W, !keep};
+
+    if (h_span_start[path] > h_span_end[path] || h_span_end[path] > n_steps) return FGFA_ERR_SPAN_OOB;
+    const uint32_t n = h_span_end[path] - h_span_start[path];
+    // aux: [seg_end u64 x n][scan scratch for the step offsets]
+    const size_t off_bytes = up256(std::max<size_t>((size_t)n * 8, 8));
+    const size_t scr1 = fgfa_interval_scratch_bytes(n, 0);
+    int rc = ensure_workspace(W, n_steps, n_segs, off_bytes + scr1);
+    if (rc) return rc;
+    const uint64_t key[4] = {n_paths, n_segs, n_steps,
+                             fnv1a(h_span_end, n_paths, fnv1a(h_span_start, n_paths, 0xCBF29CE484222325ull))};
+    if (!W.plan || std::memcmp(key, W.plan_key, sizeof key) != 0) {
+        if (W.plan) fgfa_depth_plan_destroy(W.plan);
+        W.plan = nullptr;
+        rc = fgfa_depth_plan_create(&W.plan, h_span_start, h_span_end, n_paths, n_segs, n_steps, 0);
+        if (rc) return rc;
+        std::memcpy(W.plan_key, key, sizeof key);
+    }
+    uint32_t* d_depth = W.out;
+    uint32_t* d_len = W.out + n_segs;
+    uint64_t* d_seg_end = static_cast<uint64_t*>(W.aux);
+    void* d_scr1 = static_cast<char*>(W.aux) + off_bytes;
+    const uint32_t* d_path = W.steps + h_span_start[path];
+    if (n_steps) CUH(cudaMemcpyAsync(W.steps, h_steps, (size_t)n_steps * 4, cudaMemcpyHostToDevice, W.compute));
+    if (n_segs) CUH(cudaMemcpyAsync(d_len, h_seg_len, (size_t)n_segs * 4, cudaMemcpyHostToDevice, W.compute));
+    rc = fgfa_depth_plan_run(W.plan, W.steps, d_depth, nullptr, W.compute);                 // window_depth.rs:177
+    if (rc) return rc;
+    rc = fgfa_path_offsets_device(d_path, n, d_len, n_segs, d_seg_end, d_scr1, scr1, W.compute);
+    if (rc) return rc;
+    uint64_t total = 0;                                                                     // path_length, :69-77
+    if (n) CUH(cudaMemcpyAsync(&total, d_seg_end + (n - 1), 8, cudaMemcpyDeviceToHost, W.compute));
+    rc = fgfa_depth_plan_status(W.plan, W.compute);    // synchronises; reports OOB segments
+    if (rc) return rc;
+    if (path_length_out) *path_length_out = total;
+
+    uint64_t m = n_intervals;
+    if (uniform) {
+        m = total / window_size + (total % window_size ? 1 : 0);                            // Windows::len, :59-61
+        if (n_windows_out) *n_windows_out = m;
+        *depth_alloc = static_cast<double*>(std::malloc(std::max<size_t>((size_t)m * 8, 8)));
+        if (!*depth_alloc) return FGFA_ERR_NOMEM;
+        depth_out = *depth_alloc;
+    }
+    if (m == 0) return FGFA_OK;
+    // aux2: [win_start u64 x m][win_end u64 x m][out f64 x m][scratch]
+    const size_t col = up256((size_t)m * 8);
+    const size_t scr2 = fgfa_interval_scratch_bytes(n, m);
+    if (W.aux2_cap < 3 * col + scr2) {
+        cudaFree(W.aux2); W.aux2 = nullptr; W.aux2_cap = 0;
+        rc = cuda_rc(cudaMalloc(&W.aux2, 3 * col + scr2));
+        if (rc) { if (uniform) { std::free(*depth_alloc); *depth_alloc = nullptr; } return rc; }
+        W.aux2_cap = 3 * col + scr2;
+    }
+    uint64_t* d_ws = static_cast<uint64_t*>(W.aux2);
+    uint64_t* d_we = reinterpret_cast<uint64_t*>(static_cast<char*>(W.aux2) + col);
+    double* d_out = reinterpret_cast<double*>(static_cast<char*>(W.aux2) + 2 * col);
+    void* d_scr2 = static_cast<char*>(W.aux2) + 3 * col;
+    auto bail = [&](int code) { if (uniform) { std::free(*depth_alloc); *depth_alloc = nullptr; } return code; };
+    if (uniform) {
+        rc = fgfa_make_windows_device(0, total, window_size, m, d_ws, d_we, W.compute);     // :188-194
+        if (rc) return bail(rc);
+    } else {
+        if ((rc = cuda_rc(cudaMemcpyAsync(d_ws, h_win_start, (size_t)m * 8, cudaMemcpyHostToDevice, W.compute)))) return rc;
+        if ((rc = cuda_rc(cudaMemcpyAsync(d_we, h_win_end, (size_t)m * 8, cudaMemcpyHostToDevice, W.compute)))) return rc;
+    }
+    if ((rc = cuda_rc(cudaMemsetAsync(d_scr2, 0, 4, W.compute)))) return bail(rc);
+    rc = fgfa_interval_depth_device(d_path, n, d_depth, d_len, n_segs, d_seg_end, d_ws, d_we, m, d_out, d_scr2,
+                                    scr2, W.compute);
+    if (rc) return bail(rc);
+    if ((rc = cuda_rc(cudaMemcpyAsync(depth_out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, W.compute)))) return bail(rc);
+    rc = fgfa_interval_status(d_scr2, W.compute);
+    if (rc) return bail(rc);
+    return FGFA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int fgfa_interval_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint32_t* h_span_start,
+                              const uint32_t* h_span_end, uint32_t n_paths, const uint32_t* h_seg_len,
+                              uint32_t n_segs, uint32_t path, const uint64_t* h_win_start,
+                              const uint64_t* h_win_end, uint64_t n_intervals, double* depth_out) {
+    return interval_depth_host(h_steps, n_steps, h_span_start, h_span_end, n_paths, h_seg_len, n_segs, path,
+                               h_win_start, h_win_end, n_intervals, 0, depth_out, nullptr, nullptr, nullptr);
+}
+
+int fgfa_window_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint32_t* h_span_start,
+                            const uint32_t* h_span_end, uint32_t n_paths, const uint32_t* h_seg_len,
+                            uint32_t n_segs, uint32_t path, uint64_t window_size, double** depth_out,
+                            uint64_t* n_windows_out, uint64_t* path_length_out) {
+    if (!depth_out) return FGFA_ERR_INVALID_ARG;
+    *depth_out = nullptr;
+    if (n_windows_out) *n_windows_out = 0;
+    return interval_depth_host(h_steps, n_steps, h_span_start, h_span_end, n_paths, h_seg_len, n_segs, path,
+                               nullptr, nullptr, 0, window_size, nullptr, depth_out, n_windows_out, path_length_out);
+}
+
+void fgfa_free(void* p) { std::free(p); }
 
 }  // extern "C"
 

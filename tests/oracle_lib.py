@@ -31,6 +31,21 @@ def oracle():
         h.oracle_format_float.restype = C.c_int
         h.oracle_format_float.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_size_t]
 
+        h.oracle_window_count.restype = C.c_uint64
+        h.oracle_window_count.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        h.oracle_make_windows.restype = None
+        h.oracle_make_windows.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        h.oracle_path_length.restype = C.c_uint64
+        h.oracle_path_length.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        h.oracle_interval_depth.restype = C.c_int
+        h.oracle_interval_depth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                            C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        h.oracle_parse_bed.restype = C.c_int64
+        h.oracle_parse_bed.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        h.oracle_emit_interval_depth.restype = C.c_int64
+        h.oracle_emit_interval_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                 C.c_char_p, C.c_uint64]
+
         class View(C.Structure):
             _fields_ = [(n, C.c_uint64) for n in ("n_segs", "n_paths", "n_steps", "segs_off", "paths_off", "steps_off")]
 
@@ -79,6 +94,63 @@ def path_depth(steps, start, end, seg_len, path_ids=None):
                                     seg_len.size, None if ids is None else ids.ctypes.data, n,
                                     lengths.ctypes.data, means.ctypes.data)
     return rc, lengths, means
+
+
+def interval_depth(steps, start, end, seg_len, path, win_start, win_end):
+    """oracle_interval_depth -> (rc, depths f64)."""
+    steps = np.ascontiguousarray(steps, dtype=np.uint32)
+    seg_len = np.ascontiguousarray(seg_len, dtype=np.uint32)
+    sp = spans_of(start, end)
+    ws = np.ascontiguousarray(win_start, dtype=np.uint64)
+    we = np.ascontiguousarray(win_end, dtype=np.uint64)
+    out = np.empty(ws.size, dtype=np.float64)
+    rc = oracle().oracle_interval_depth(steps.ctypes.data, steps.size, sp.ctypes.data, len(start), seg_len.ctypes.data,
+                                        seg_len.size, path, ws.ctypes.data, we.ctypes.data, ws.size, out.ctypes.data)
+    return rc, out
+
+
+def windows(start, end, size):
+    """oracle_window_count + oracle_make_windows -> (win_start u64, win_end u64)."""
+    m = int(oracle().oracle_window_count(start, end, size))
+    ws = np.empty(m, dtype=np.uint64)
+    we = np.empty(m, dtype=np.uint64)
+    oracle().oracle_make_windows(start, end, size, ws.ctypes.data, we.ctypes.data)
+    return ws, we
+
+
+def path_length(steps, start, end, seg_len, path):
+    steps = np.ascontiguousarray(steps, dtype=np.uint32)
+    seg_len = np.ascontiguousarray(seg_len, dtype=np.uint32)
+    sp = spans_of(start, end)
+    return int(oracle().oracle_path_length(steps.ctypes.data, sp.ctypes.data, path, seg_len.ctypes.data))
+
+
+def parse_bed(text: bytes):
+    """oracle_parse_bed -> None where the reference panics, else [(name bytes, start, end)]."""
+    buf = np.frombuffer(text, dtype=np.uint8)
+    cap = text.count(b"\n") + 1
+    cols = [np.empty(cap, dtype=np.uint64) for _ in range(4)]
+    n = oracle().oracle_parse_bed(buf.ctypes.data if buf.size else None, buf.size, *[c.ctypes.data for c in cols], cap)
+    if n < 0:
+        return None
+    return [(text[int(cols[0][i]):int(cols[0][i] + cols[1][i])], int(cols[2][i]), int(cols[3][i])) for i in range(n)]
+
+
+def emit_interval_depth(entries, depths) -> bytes:
+    """window_depth.rs:163-174 through oracle_emit_interval_depth; entries = [(name bytes, start, end)]."""
+    names = b"".join(e[0] for e in entries)
+    off = np.cumsum([0] + [len(e[0]) for e in entries[:-1]], dtype=np.uint64) if entries else np.empty(0, np.uint64)
+    ln = np.array([len(e[0]) for e in entries], dtype=np.uint64)
+    s = np.array([e[1] for e in entries], dtype=np.uint64)
+    t = np.array([e[2] for e in entries], dtype=np.uint64)
+    d = np.ascontiguousarray(depths, dtype=np.float64)
+    cap = 64 + sum(len(e[0]) + 500 for e in entries)
+    out = C.create_string_buffer(cap)
+    nb = np.frombuffer(names, dtype=np.uint8)
+    k = oracle().oracle_emit_interval_depth(nb.ctypes.data if nb.size else None, off.ctypes.data, ln.ctypes.data, s.ctypes.data,
+                                            t.ctypes.data, d.ctypes.data, len(entries), out, cap)
+    assert k >= 0
+    return out.raw[:k]
 
 
 def format_float(x: float, digits: int = 2) -> str:

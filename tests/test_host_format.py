@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported():
     for h in ("fgfa_depth.h", "flatgfa.h"):
         text = open(os.path.join(ROOT, "include", h), encoding="utf-8").read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        declared |= set(re.findall(r"\b((?:fgfa|flatgfa)_[a-z0-9_]+)\s*\(", text))
+        declared |= set(re.findall(r"\b((?:fgfa|flatgfa|flatbed)_[a-z0-9_]+)\s*\(", text))
     assert len(declared) >= 30
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"

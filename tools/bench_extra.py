@@ -66,6 +66,35 @@ def main():
         cpu_path = time.perf_counter() - t0
         got = sums.cpu().numpy().view(np.uint64)
         assert rc == 0 and (got[1::2] == ol).all()
+        # window-depth mode (window_depth.rs:183-197) along path 0, 1000 bp windows: depth-only run + W1..W3
+        wpath, wsize = 0, 1000
+        n_path = int(e[wpath] - s[wpath])
+        total = O.path_length(steps, s, e, seg_len, wpath)
+        n_win = (total + wsize - 1) // wsize
+        seg_end = torch.empty(max(n_path, 1), dtype=torch.int64, device="cuda")
+        wins = torch.empty(3 * max(n_win, 1), dtype=torch.int64, device="cuda")
+        d_win = torch.empty(max(n_win, 1), dtype=torch.float64, device="cuda")
+        scr_bytes = lib.fgfa_interval_scratch_bytes(n_path, n_win)
+        scr = torch.empty(scr_bytes, dtype=torch.uint8, device="cuda")
+        d_path = d_steps.data_ptr() + 4 * int(s[wpath])
+        ws_ptr, we_ptr = wins.data_ptr(), wins.data_ptr() + 8 * max(n_win, 1)
+
+        def interval_kernels():
+            rc = lib.fgfa_path_offsets_device(d_path, n_path, d_len.data_ptr(), cfg.n_segs, seg_end.data_ptr(),
+                                              scr.data_ptr(), scr_bytes, st.cuda_stream)
+            rc = rc or lib.fgfa_make_windows_device(0, total, wsize, n_win, ws_ptr, we_ptr, st.cuda_stream)
+            rc = rc or lib.fgfa_interval_depth_device(d_path, n_path, out.data_ptr(), d_len.data_ptr(), cfg.n_segs,
+                                                      seg_end.data_ptr(), ws_ptr, we_ptr, n_win, d_win.data_ptr(),
+                                                      scr.data_ptr(), scr_bytes, st.cuda_stream)
+            assert rc == 0
+        plan.run(d_steps, out[: cfg.n_segs], None, st.cuda_stream)
+        wkern = timed(interval_kernels, st)
+        assert lib.fgfa_interval_status(scr.data_ptr(), st.cuda_stream) == 0
+        ows, owe = O.windows(0, total, wsize)
+        t0 = time.perf_counter()
+        rc, owd = O.interval_depth(steps, s, e, seg_len, wpath, ows, owe)
+        cpu_window = time.perf_counter() - t0
+        assert rc == 0 and d_win.cpu().numpy()[:n_win].tobytes() == owd.tobytes()
         t0 = time.perf_counter()
         rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
         cpu_node = time.perf_counter() - t0
@@ -80,6 +109,8 @@ def main():
             "node_depth_frac_of_measured_hbm": alg / (full * 1e-3) / 1e9 / peak,
             "depth_only_ms": donly, "depth_only_frac_of_measured_hbm": (alg - 4.0 * cfg.n_segs) / (donly * 1e-3) / 1e9 / peak,
             "path_depth_ms": pmode, "path_measure_kernel_ms": pmode - donly,
+            "window_depth_ms": donly + wkern, "interval_kernels_ms": wkern, "window_path_steps": n_path, "windows": int(n_win),
+            "cpu_window_depth_s_1core": cpu_window,
             "cpu_node_depth_s_1core": cpu_node, "cpu_path_depth_s_1core": cpu_path, "parity": "bit-exact"}))
         plan.close()
         del d_steps, out, scratch
