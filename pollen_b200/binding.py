@@ -64,6 +64,9 @@ EXPORTS = {
     "flatgfa_path_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "flatgfa_format_path_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "flatgfa_dump": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "flatgfa_parse_mem": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+    "flatgfa_image_size": (C.c_size_t, [C.c_void_p]),
+    "flatgfa_dump_mem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "flatbed_parse_mem": (C.c_void_p, [C.c_void_p, C.c_size_t]),
     "flatbed_make_windows": (C.c_void_p, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64]),
     "flatbed_free": (None, [C.c_void_p]),
@@ -305,6 +308,18 @@ class FlatGFA:
     @classmethod
     def parse(cls, gfa_path: str) -> "FlatGFA":  # flatgfa_parse, lib.rs:62-68
         return cls(lib().flatgfa_parse(os.fsencode(gfa_path)))
+
+    @classmethod
+    def parse_bytes(cls, gfa_text: bytes) -> "FlatGFA":  # flatgfa-py parse_bytes, lib.rs:69-71
+        buf = C.create_string_buffer(gfa_text, len(gfa_text))
+        return cls(lib().flatgfa_parse_mem(C.cast(buf, C.c_void_p), len(gfa_text)))
+
+    def image(self) -> np.ndarray:
+        """The graph's .flatgfa image (``file::dump``, file.rs:290-307) as a uint8 array."""
+        n = int(lib().flatgfa_image_size(self._h))
+        out = np.empty(n, dtype=np.uint8)
+        _check(lib().flatgfa_dump_mem(self._h, out.ctypes.data, n))
+        return out
 
     @classmethod
     def load(cls, flatgfa_path: str) -> "FlatGFA":  # memfile::map_file + file::view

@@ -295,6 +295,32 @@ int flatgfa_bed_depth(flatgfa_t gfa, const uint8_t* bed_text, size_t bed_len, ch
     }
 }
 
+flatgfa_t flatgfa_parse_mem(const uint8_t* gfa_text, size_t len) {
+    if (len && !gfa_text) { g_err = "null text"; return nullptr; }
+    try {
+        std::unique_ptr<CStore> s(new CStore());
+        s->heap = flatgfa::Parser::parse_mem(gfa_text, len);
+        s->gfa = s->heap.view();
+        return s.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+size_t flatgfa_image_size(flatgfa_t gfa) { return gfa ? flatgfa::file::size(gfa->gfa) : 0; }
+
+int flatgfa_dump_mem(flatgfa_t gfa, uint8_t* buf, size_t cap) {
+    if (!gfa || !buf || cap < flatgfa::file::size(gfa->gfa)) return FGFA_ERR_INVALID_ARG;
+    try {
+        flatgfa::file::dump(gfa->gfa, buf);
+        return FGFA_OK;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return FGFA_ERR_INVALID_ARG;
+    }
+}
+
 int flatgfa_dump(flatgfa_t gfa, const char* filename) {
     if (!gfa || !filename) return FGFA_ERR_INVALID_ARG;
     try {
