@@ -12,7 +12,7 @@ OBJDIR    := build/obj
 
 LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(OBJDIR)/ops_depth.o $(OBJDIR)/ops_window_depth.o $(OBJDIR)/flatbed.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/capi.o
 
-all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools
+all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libflatgfa.a $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools
 
 $(OBJDIR)/depth_device.o: $(CSRC)/depth_device.cu $(CSRC)/depth_kernels.cuh include/fgfa_depth.h
 	@mkdir -p $(OBJDIR)
@@ -33,6 +33,12 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.hpp) include/fgfa_depth.h incl
 $(LIBDIR)/libflatgfa.so: $(LIB_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS) -cudart static -lpthread
+
+# flatgfa-c/Cargo.toml:6-8 builds both a cdylib and a staticlib; link the archive with
+#   g++ app.o libflatgfa.a -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+$(LIBDIR)/libflatgfa.a: $(LIB_OBJS)
+	@mkdir -p $(LIBDIR)
+	rm -f $@ && ar rcs $@ $(LIB_OBJS)
 
 $(LIBDIR)/libfgfa_synth.so: $(CSRC)/synth.cpp
 	@mkdir -p $(LIBDIR)
@@ -55,6 +61,6 @@ build/ubench: tools/ubench.cu tools/experimental_kernels.cuh $(CSRC)/depth_kerne
 	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench.cu build/depth_oracle.o build/synth.o -o $@
 
 clean:
-	rm -rf build bin $(LIBDIR)/*.so oracle/*.so
+	rm -rf build bin $(LIBDIR)/*.so $(LIBDIR)/*.a oracle/*.so
 
 .PHONY: all oracle tools clean
