@@ -10,7 +10,7 @@ CSRC      := pollen_b200/csrc
 LIBDIR    := pollen_b200/lib
 OBJDIR    := build/obj
 
-LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(OBJDIR)/ops_depth.o $(OBJDIR)/ops_window_depth.o $(OBJDIR)/flatbed.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/capi.o
+LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(OBJDIR)/ops_depth.o $(OBJDIR)/ops_window_depth.o $(OBJDIR)/flatbed.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/print.o $(OBJDIR)/capi.o
 
 all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libflatgfa.a $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools
 

@@ -64,6 +64,7 @@ EXPORTS = {
     "flatgfa_path_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "flatgfa_format_path_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "flatgfa_dump": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "flatgfa_format_gfa": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "flatgfa_parse_mem": (C.c_void_p, [C.c_void_p, C.c_size_t]),
     "flatgfa_image_size": (C.c_size_t, [C.c_void_p]),
     "flatgfa_dump_mem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -368,6 +369,15 @@ class FlatGFA:
 
     def dump(self, flatgfa_path: str) -> None:
         _check(lib().flatgfa_dump(self._h, os.fsencode(flatgfa_path)))
+
+    def format_gfa(self) -> bytes:
+        """The graph as GFA text (print.rs:144-152)."""
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().flatgfa_format_gfa(self._h, C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            C.CDLL(None).free(out)
 
     def seg_depth_with_uniq(self) -> Tuple[np.ndarray, np.ndarray]:
         n = self.segment_count

@@ -12,6 +12,7 @@
 #include "ops_depth.hpp"
 #include "ops_window_depth.hpp"
 #include "parse.hpp"
+#include "print.hpp"
 
 // lib.rs:16: the opaque store behind flatgfa_t.  Either a parsed heap store or a
 // zero-copy view of a mapped .flatgfa file.
@@ -315,6 +316,18 @@ int flatgfa_dump_mem(flatgfa_t gfa, uint8_t* buf, size_t cap) {
     try {
         flatgfa::file::dump(gfa->gfa, buf);
         return FGFA_OK;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return FGFA_ERR_INVALID_ARG;
+    }
+}
+
+int flatgfa_format_gfa(flatgfa_t gfa, char** out, size_t* out_len) {
+    if (!gfa || !out || !out_len) return FGFA_ERR_INVALID_ARG;
+    try {
+        std::string s;
+        flatgfa::print::gfa(gfa->gfa, s);
+        return text_out(s, out, out_len);
     } catch (const std::exception& e) {
         g_err = e.what();
         return FGFA_ERR_INVALID_ARG;

@@ -8,6 +8,7 @@
 //   fgfa [-i FLATGFA | -I GFA | < GFA] depth -b BED      interval depth table (cmds.rs:246-255)
 //   fgfa [-i FLATGFA | -I GFA | < GFA] window-depth PATH SIZE   (cmds.rs:477-496)
 //   fgfa [-i FLATGFA | -I GFA | < GFA] -o OUT.flatgfa    convert to the binary format
+//   fgfa [-i FLATGFA | -I GFA | < GFA] [-O OUT.gfa]      GFA text to a file or stdout (print.rs)
 // The other subcommands of the reference are outside this repository's scope
 // and are rejected with an error.
 #include <cstdio>
@@ -21,6 +22,7 @@
 #include "ops_depth.hpp"
 #include "ops_window_depth.hpp"
 #include "parse.hpp"
+#include "print.hpp"
 
 namespace {
 
@@ -163,8 +165,14 @@ int main(int argc, char** argv) {
             flatgfa::write_file(a.output, buf.data(), buf.size());
             return 0;
         }
-        std::fprintf(stderr, "fgfa: GFA text output is outside the scope of this build; use -o <file.flatgfa>\n");
-        return 1;
+        std::string text;
+        flatgfa::print::gfa(gfa, text);                                       // main.rs:201-211
+        if (!a.output_gfa.empty()) {
+            flatgfa::write_file(a.output_gfa, reinterpret_cast<const uint8_t*>(text.data()), text.size());
+        } else {
+            std::fwrite(text.data(), 1, text.size(), stdout);
+        }
+        return 0;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "Error: %s\n", e.what());
         return 1;
