@@ -72,3 +72,23 @@ def test_oracle_and_product_parser_match_slow_odgi(tmp_path_factory, text):
     subprocess.run([os.path.join(ROOT, "bin", "fgfa"), "-I", str(src), "-o", str(flat)], check=True)
     rc, fnames, fd, fu = O.file_depth(flat.read_bytes())
     assert rc == 0 and O.emit(fnames, fd, fu) == want
+
+
+def test_every_reference_gfa_fixture_round_trips(tmp_path):
+    """The reference's own round-trip harness (tests/turnt.toml:162-172, envs flatgfa_mem and
+    flatgfa_file) over every GFA file in the reference checkout."""
+    import glob
+
+    fgfa = os.path.join(ROOT, "bin", "fgfa")
+    files = sorted(glob.glob(os.path.join(REF, "tests", "**", "*.gfa"), recursive=True)) + \
+        sorted(glob.glob(os.path.join(REF, "flatgfa-py", "test", "*.gfa")))
+    assert len(files) >= 8
+    for f in files:
+        text = open(f, "rb").read()
+        want = text if text.endswith(b"\n") else text[: text.rfind(b"\n") + 1]   # parse_mem drops an unterminated last line
+        got = subprocess.run([fgfa, "-I", f], capture_output=True)
+        assert got.returncode == 0, (f, got.stderr)
+        assert got.stdout == want, f
+        flat = str(tmp_path / "t.flatgfa")
+        subprocess.run([fgfa, "-I", f, "-o", flat], check=True)
+        assert subprocess.run([fgfa, "-i", flat], capture_output=True, check=True).stdout == want, f
