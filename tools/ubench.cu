@@ -97,6 +97,31 @@ int main(int argc, char** argv) {
         uint64_t a = ss[p] & ~3u;
         for (uint32_t c = prefix[p]; c < prefix[p + 1]; ++c, a += kChunk) table[c] = ChunkDesc{(uint32_t)a, ss[p], se[p], p};
     }
+    // experiment: the ORDER of the chunk table decides which chunks run concurrently (kernel A walks it
+    // with stride gridDim.x).  UBENCH_PERMUTE=contig:<grid> gives every CTA a contiguous share of the
+    // original order, UBENCH_PERMUTE=random shuffles it.
+    if (const char* pm = getenv("UBENCH_PERMUTE")) {
+        std::vector<ChunkDesc> t2;
+        t2.reserve(n_chunks);
+        if (!strncmp(pm, "contig:", 7)) {
+            const uint32_t G = (uint32_t)atoi(pm + 7);
+            const uint32_t per = (n_chunks + G - 1) / G;
+            for (uint32_t r = 0; r < per; ++r)
+                for (uint32_t b = 0; b < G; ++b) {
+                    const uint64_t i = (uint64_t)b * per + r;
+                    if (i < n_chunks) t2.push_back(table[i]);
+                }
+        } else {
+            t2 = table;
+            uint64_t x = 0x9E3779B97F4A7C15ull;
+            for (size_t i = t2.size(); i > 1; --i) {
+                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+                std::swap(t2[i - 1], t2[x % i]);
+            }
+        }
+        table.swap(t2);
+        printf("chunk table permuted: %s\n", pm);
+    }
     ChunkDesc* d_chunks;
     CK(cudaMalloc(&d_chunks, std::max<size_t>(n_chunks, 1) * sizeof(ChunkDesc)));
     CK(cudaMemcpy(d_chunks, table.data(), (size_t)n_chunks * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
