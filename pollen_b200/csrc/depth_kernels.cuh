@@ -511,7 +511,10 @@ __global__ void __launch_bounds__(256) k_interleave_depth_len(const uint32_t* __
     if (i < n) out[i] = make_uint2(depth[i], len[i]);
 }
 
-__global__ void __launch_bounds__(kThreads) k_path_measure(MeasureParams P) {
+// 8 resident CTAs per SM (32 registers): the kernel is latency-bound and lives on occupancy —
+// caps of 6 / 5 / 4 CTAs measured 0.50 / 0.59 / 0.72 ms against 0.44 ms; ld.global.cg gathers measured
+// the same as ld.global.nc, L1::no_allocate 0.54 ms.
+__global__ void __launch_bounds__(kThreads, 8) k_path_measure(MeasureParams P) {
     __shared__ unsigned long long s_part[2][kThreads / 32];
     const uint64_t pol = make_evict_first_policy();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
