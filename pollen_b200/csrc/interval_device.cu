@@ -24,20 +24,25 @@ constexpr size_t kAlign = 256;
 size_t round_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 uint64_t tiles_of(uint64_t n) { return (n + fgfa::kScanTile - 1) / fgfa::kScanTile; }
 
-// scratch layout: [err u32, padded][tile totals u64 x max(tiles(n), tiles(m))][lb/fin u32 x m]
+// scratch layout: [err u32, long_count u32, padded][tile totals u64 x max(tiles(n), tiles(m))][lb/fin u32 x m][long list u32 x m]
 struct Scratch {
     uint32_t* err;
+    uint32_t* long_count;
     uint64_t* tile_totals;
     uint32_t* fin;
+    uint32_t* long_list;
 };
 Scratch carve(void* base, uint64_t n, uint64_t m) {
     char* p = static_cast<char*>(base);
     Scratch s;
     s.err = reinterpret_cast<uint32_t*>(p);
+    s.long_count = s.err + 1;
     p += kAlign;
     s.tile_totals = reinterpret_cast<uint64_t*>(p);
     p += round_up(std::max<uint64_t>(1, std::max(tiles_of(n), tiles_of(m))) * 8);
     s.fin = reinterpret_cast<uint32_t*>(p);
+    p += round_up(std::max<uint64_t>(1, m) * 4);
+    s.long_list = reinterpret_cast<uint32_t*>(p);
     return s;
 }
 
@@ -71,7 +76,7 @@ extern "C" {
 
 size_t fgfa_interval_scratch_bytes(uint64_t n_path_steps, uint64_t n_intervals) {
     return kAlign + round_up(std::max<uint64_t>(1, std::max(tiles_of(n_path_steps), tiles_of(n_intervals))) * 8) +
-           round_up(std::max<uint64_t>(1, n_intervals) * 4);
+           2 * round_up(std::max<uint64_t>(1, n_intervals) * 4);
 }
 
 int fgfa_path_offsets_device(const uint32_t* d_path_steps, uint32_t n, const uint32_t* d_seg_len,
@@ -106,10 +111,11 @@ int fgfa_interval_depth_device(const uint32_t* d_path_steps, uint32_t n, const u
     if (m == 0) return FGFA_OK;
     if (!d_win_start || !d_win_end || !d_out) return FGFA_ERR_INVALID_ARG;
     if (n && (!d_path_steps || !d_depth || !d_seg_len || !d_seg_end)) return FGFA_ERR_INVALID_ARG;
-    if ((m + 255) / 256 > 0x7FFFFFFFull) return FGFA_ERR_TOO_LARGE;
+    if (m > 0xFFFFFFFFull) return FGFA_ERR_TOO_LARGE;            // the worklist holds u32 interval indices
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const Scratch S = carve(d_scratch, n, m);
     const unsigned grid = (unsigned)((m + 255) / 256);
+    CI(cudaMemsetAsync(S.long_count, 0, 4, st));
     fgfa::k_interval_lower_bound<<<grid, 256, 0, st>>>(d_seg_end, n, d_win_end, m, S.fin);
     CI(cudaGetLastError());
     // the cursor of assign_depths never moves backwards: fin = running maximum of lb
@@ -127,7 +133,13 @@ int fgfa_interval_depth_device(const uint32_t* d_path_steps, uint32_t n, const u
     P.n_win = m;
     P.fin = S.fin;
     P.out = d_out;
+    P.long_list = S.long_list;
+    P.long_count = S.long_count;
     fgfa::k_interval_accumulate<<<grid, 256, 0, st>>>(P);
+    CI(cudaGetLastError());
+    // one warp per long interval; the count stays on the device (an empty list costs one idle launch)
+    const unsigned long_grid = (unsigned)std::min<uint64_t>((m + 7) / 8, (uint64_t)sm_count() * 8);
+    fgfa::k_interval_accumulate_long<<<long_grid, 256, 0, st>>>(P);
     CI(cudaGetLastError());
     return FGFA_OK;
 }

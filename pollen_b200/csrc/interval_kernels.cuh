@@ -17,8 +17,8 @@
 //       inclusive: the step that finishes w-1 is offered to w too, window_depth.rs:128-150), summed in
 //       step order with the reference's exact f64 operation sequence (u64 -> f64 conversions,
 //       one divide, one multiply, one divide, one add; no contraction), so the result is bit-exact.
-// Short intervals are summed one per thread; long ones by the whole warp (lanes form the terms in
-// parallel, the additions stay in order).
+// Short intervals are summed one per thread (W3a); long ones go to a worklist and are summed one per
+// warp (W3b: lanes form the terms in parallel, the additions stay in order).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -208,6 +208,8 @@ struct IntervalParams {
     uint64_t n_win;
     const uint32_t* __restrict__ fin;        // [n_win] W2
     double* __restrict__ out;                // [n_win]
+    uint32_t* __restrict__ long_list;        // [n_win] intervals left to W3b
+    uint32_t* __restrict__ long_count;       // zero on entry
 };
 
 constexpr uint32_t kLongInterval = 48;       // steps; longer intervals are summed by the whole warp
@@ -229,56 +231,73 @@ __device__ __forceinline__ bool interval_term(const IntervalParams& P, uint32_t 
     return true;
 }
 
+// The range of steps interval w is offered (see W3 above); empty ranges come back as j0 > j1.
+__device__ __forceinline__ void interval_range(const IntervalParams& P, uint64_t w, uint32_t& j0, uint32_t& j1) {
+    j0 = 1;
+    j1 = 0;
+    if (P.n) {
+        const uint32_t a = w ? P.fin[w - 1] : 0u;
+        const uint32_t f = P.fin[w];
+        const uint32_t b = f < P.n ? f : P.n - 1;
+        if (a <= b) { j0 = a; j1 = b; }
+    }
+}
+
+// W3a: one thread per interval.  Short intervals are summed here; long ones (>= kLongInterval
+// steps) are appended to a worklist for W3b, so that a BED file with a few chromosome-sized
+// intervals still spreads over the whole GPU instead of serialising inside one warp.
 __global__ void __launch_bounds__(256) k_interval_accumulate(IntervalParams P) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t w_warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(uint64_t)31;
-    if (w_warp >= P.n_win) return;                               // warp-uniform
-    const uint64_t w = w_warp + lane;
-    const bool live = w < P.n_win;
-    uint64_t w0 = 0, w1 = 0;
-    uint32_t j0 = 1, j1 = 0;                                     // empty range
-    if (live) {
-        w0 = P.win_start[w];
-        w1 = P.win_end[w];
-        if (P.n) {
-            j0 = w ? P.fin[w - 1] : 0u;
-            const uint32_t f = P.fin[w];
-            j1 = f < P.n ? f : P.n - 1;
-            if (j0 > j1) { j0 = 1; j1 = 0; }
-        }
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= P.n_win) return;
+    const uint64_t w0 = P.win_start[w], w1 = P.win_end[w];
+    uint32_t j0, j1;
+    interval_range(P, w, j0, j1);
+    if (j1 >= j0 && (j1 - j0) >= kLongInterval) {
+        P.long_list[atomicAdd(P.long_count, 1u)] = (uint32_t)w;        // n_win <= 2^32 is enforced by the host
+        return;
     }
-    const bool is_long = live && j1 >= j0 && (j1 - j0) >= kLongInterval;
     double acc = 0.0;                                            // :119
-    if (live && !is_long) {
-        for (uint32_t j = j0; j <= j1; ++j) {          // j1 <= n-1 < 2^32-1: no wrap
-            double t;
-            if (interval_term(P, j, w0, w1, t)) acc = __dadd_rn(acc, t);   // :135
-        }
+    for (uint32_t j = j0; j <= j1; ++j) {                        // j1 <= n-1 < 2^32-1: no wrap
+        double t;
+        if (interval_term(P, j, w0, w1, t)) acc = __dadd_rn(acc, t);   // :135
     }
-    // long intervals: one at a time, the warp forms 32 terms in parallel, the sum stays in step order
-    uint32_t todo = __ballot_sync(0xFFFFFFFFu, is_long);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint64_t lw0 = __shfl_sync(0xFFFFFFFFu, w0, src);
-        const uint64_t lw1 = __shfl_sync(0xFFFFFFFFu, w1, src);
-        const uint32_t lj0 = __shfl_sync(0xFFFFFFFFu, j0, src);
-        const uint32_t lj1 = __shfl_sync(0xFFFFFFFFu, j1, src);
+    P.out[w] = acc;
+}
+
+// W3b: one warp per long interval.  The lanes form 32 terms in parallel (and already fetch the
+// next 32 while the current ones are being added); the additions stay in step order.
+__global__ void __launch_bounds__(256) k_interval_accumulate_long(IntervalParams P) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_long = *P.long_count;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n_long; idx += warps) {   // warp-uniform
+        const uint64_t w = P.long_list[idx];
+        const uint64_t w0 = P.win_start[w], w1 = P.win_end[w];
+        uint32_t j0, j1;
+        interval_range(P, w, j0, j1);
         double sum = 0.0;
-        for (uint64_t base = lj0; base <= lj1; base += 32) {     // warp-uniform trip count
-            const uint64_t j = base + lane;
-            double t = 0.0;
-            const bool ok = j <= lj1 && interval_term(P, (uint32_t)j, lw0, lw1, t);
-            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, ok);
+        uint64_t base = j0;
+        double t_next = 0.0;
+        bool ok_next = base + lane <= j1 && interval_term(P, (uint32_t)(base + lane), w0, w1, t_next);
+        while (true) {                                           // warp-uniform trip count
+            const double t = t_next;
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, ok_next);
+            const uint64_t next = base + 32;
+            const bool more = next <= j1;
+            if (more) {
+                t_next = 0.0;
+                ok_next = next + lane <= j1 && interval_term(P, (uint32_t)(next + lane), w0, w1, t_next);
+            }
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 const double tk = __shfl_sync(0xFFFFFFFFu, t, k);
                 if ((mask >> k) & 1u) sum = __dadd_rn(sum, tk);
             }
+            if (!more) break;
+            base = next;
         }
-        if ((int)lane == src) acc = sum;
+        if (lane == 0) P.out[w] = sum;
     }
-    if (live) P.out[w] = acc;
 }
 
 }  // namespace fgfa
