@@ -12,7 +12,7 @@ OBJDIR    := build/obj
 
 LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(OBJDIR)/ops_depth.o $(OBJDIR)/ops_window_depth.o $(OBJDIR)/flatbed.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/print.o $(OBJDIR)/capi.o
 
-all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libflatgfa.a $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools
+all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libflatgfa.a $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools build/depth_example
 
 $(OBJDIR)/depth_device.o: $(CSRC)/depth_device.cu $(CSRC)/depth_kernels.cuh include/fgfa_depth.h
 	@mkdir -p $(OBJDIR)
@@ -47,6 +47,11 @@ $(LIBDIR)/libfgfa_synth.so: $(CSRC)/synth.cpp
 bin/fgfa: $(CSRC)/fgfa_main.cpp $(LIBDIR)/libflatgfa.so
 	@mkdir -p bin
 	$(CXX) $(CXXFLAGS) -o $@ $< -L$(LIBDIR) -lflatgfa -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+
+# plain C client of the depth additions (compiled as C: the headers must stay C-clean)
+build/depth_example: examples/depth.c include/flatgfa.h $(LIBDIR)/libflatgfa.so
+	@mkdir -p build
+	$(CC) -std=c11 -Wall -O2 -I include examples/depth.c -L$(LIBDIR) -lflatgfa -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -o $@
 
 oracle:
 	$(MAKE) -C oracle

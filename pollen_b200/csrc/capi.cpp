@@ -133,7 +133,11 @@ int flatgfa_seg_depth(flatgfa_t gfa, uint64_t* depth, uint64_t* uniq) {
     }
     int rc = fgfa_seg_depth_with_uniq_steps(steps, g.steps.len(), s.data(), e.data(), n_paths,
                                             (uint32_t)g.segs.len(), depth, uniq);
-    if (rc) g_err = std::string(fgfa_strerror(rc)) + ": " + fgfa_last_error();
+    if (rc) {
+        g_err = fgfa_strerror(rc);
+        const char* detail = fgfa_last_error();
+        if (detail && *detail) g_err += std::string(": ") + detail;
+    }
     return rc;
 }
 

@@ -18,6 +18,7 @@ def pytest_configure(config):
         os.path.join(ROOT, "pollen_b200", "lib", "libfgfa_synth.so"),
         os.path.join(ROOT, "bin", "fgfa"),
         os.path.join(ROOT, "oracle", "libdepth_oracle.so"),
+        os.path.join(ROOT, "build", "depth_example"),
     ]
     if not all(os.path.exists(p) for p in need):
         subprocess.run(["make", "-j8", "-C", ROOT, "all"], check=True, stdout=subprocess.DEVNULL)

@@ -102,3 +102,25 @@ def test_gpu_path_depth_synthetic_exact_sums():
         ids = [cfg.n_paths - 1, 0, 0]
         l2, w2, m2 = pb.path_depth_steps(steps, s, e, seg_len, ids)
         assert (l2 == ol[ids]).all() and m2.tobytes() == om[ids].tobytes()
+
+
+def test_c_example_fails_loudly_without_a_gpu():
+    exe = os.path.join(ROOT, "build", "depth_example")
+    if pb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([exe, os.path.join(GOLD, "ref_ex2.gfa")], capture_output=True)
+    assert r.returncode == 1 and b"no CUDA device" in r.stderr and r.stdout == b""
+
+
+@pytest.mark.gpu
+def test_gpu_c_example_prints_the_three_tables():
+    """examples/depth.c (plain C over include/flatgfa.h): node table, path table, window table."""
+    exe = os.path.join(ROOT, "build", "depth_example")
+    src = os.path.join(GOLD, "ref_ex2.gfa")
+    with pb.FlatGFA.parse(src) as g:
+        d, u = g.seg_depth_with_uniq()
+        lengths, means = g.path_depth()
+        want = g.format_seg_depth(d, u) + g.format_path_depth(lengths, means) + g.window_depth("path0", 4)
+    got = subprocess.run([exe, src, "path0", "4"], capture_output=True, check=True).stdout
+    assert got == want
+    assert got.startswith(b"#node.id\tdepth\tdepth.uniq\n") and b"#path\tstart\tend\tmean.depth\n" in got
