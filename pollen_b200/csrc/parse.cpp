@@ -221,27 +221,113 @@ HeapGFAStore Parser::parse_mem(const uint8_t* buf, size_t len) {
     for (auto& d : deferred)
         if (d.first[0] == 'P') { path_bytes += d.second; ++n_path_lines; }
     const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<Builder::ParsedPath> parsed;
-    if (hw > 1 && n_path_lines > 1 && path_bytes > (4u << 20)) {
-        std::vector<size_t> idx;
-        for (size_t i = 0; i < deferred.size(); ++i)
-            if (deferred[i].first[0] == 'P') idx.push_back(i);
-        parsed.resize(idx.size());
+    if (!(hw > 1 && path_bytes > (4u << 20))) {
+        for (auto& d : deferred) {
+            if (d.first[0] == 'L') b.link(d.first, d.second);
+            else b.path(d.first, d.second);
+        }
+        return std::move(b.flat);
+    }
+    // Threaded route.  Every P line is split into its fields up front (cheap, serial); the step
+    // lists are cut into pieces of about kPieceBytes at commas that follow an orientation sign --
+    // where StepsParser is back in its initial state -- so that one very long path spreads over
+    // the workers as well as many short ones do.  A piece that is not the last of its field must
+    // end cleanly (no early stop): wherever the sequential parser would have stopped, `rest` is
+    // non-empty and parse.rs:155 fails the same way.
+    constexpr size_t kPieceBytes = 1u << 20;
+    struct Line {
+        Cursor name{nullptr, 0};
+        std::vector<std::vector<AlignOp>> overlaps;
+        std::string error;
+        size_t first_piece = 0, n_pieces = 0;
+    };
+    struct Piece {
+        const uint8_t* p;
+        size_t n;
+        bool last;
+        std::vector<Handle> steps;
+        std::string error;
+    };
+    std::vector<Line> lines;
+    std::vector<Piece> pieces;
+    for (auto& d : deferred) {
+        if (d.first[0] != 'P') continue;
+        Line ln;
+        try {                                                   // gfaline.rs:88-100, as in parse_path
+            Cursor c = Builder::body(d.first, d.second);
+            ln.name = parse_field(c);
+            Cursor steps = parse_field(c);
+            ln.overlaps = parse_maybe_overlap_list(c);
+            if (!c.empty()) throw Error("expected end of line");
+            ln.first_piece = pieces.size();
+            size_t a = 0;
+            while (true) {
+                size_t cut = steps.n;                           // default: the rest of the field
+                if (steps.n - a > kPieceBytes + (kPieceBytes >> 2)) {
+                    for (size_t q = a + kPieceBytes; q + 1 < steps.n; ++q)
+                        if (steps.p[q] == ',' && (steps.p[q - 1] == '+' || steps.p[q - 1] == '-')) { cut = q; break; }
+                }
+                const bool last = cut == steps.n;
+                pieces.push_back(Piece{steps.p + a, cut - a, last, {}, {}});
+                if (last) break;
+                a = cut + 1;                                    // the comma itself is consumed here
+            }
+            ln.n_pieces = pieces.size() - ln.first_piece;
+        } catch (const std::exception& e) {
+            ln.error = e.what();
+        }
+        lines.push_back(std::move(ln));
+    }
+    {
         std::atomic<size_t> next{0};
         auto work = [&]() {
-            for (size_t k; (k = next.fetch_add(1)) < idx.size();)
-                parsed[k] = b.parse_path(deferred[idx[k]].first, deferred[idx[k]].second);
+            for (size_t k; (k = next.fetch_add(1)) < pieces.size();) {
+                Piece& pc = pieces[k];
+                try {
+                    pc.steps.reserve(pc.n / 3 + 1);
+                    bool clean = false;
+                    const size_t used = parse_steps(pc.p, pc.n, [&](uint64_t seg, bool fwd) {
+                        pc.steps.push_back(Handle::make(b.seg_ids.get(seg), fwd));
+                    }, &clean);
+                    if (pc.last ? used != pc.n : !clean) throw Error("malformed step list");   // parse.rs:155 assert
+                } catch (const std::exception& e) {
+                    pc.error = e.what();
+                }
+            }
         };
         std::vector<std::thread> pool;
-        for (unsigned t = 1; t < std::min<size_t>(hw, idx.size()); ++t) pool.emplace_back(work);
+        for (unsigned t = 1; t < std::min<size_t>(hw, pieces.size()); ++t) pool.emplace_back(work);
         work();
         for (auto& t : pool) t.join();
     }
-    size_t k = 0;
+    // parse.rs:110-123: links and paths are added in file order; the first failure in that order wins.
+    const size_t base = b.flat.steps.size();
+    size_t running = base, k = 0;
+    std::vector<size_t> piece_off(pieces.size(), 0);
     for (auto& d : deferred) {
-        if (d.first[0] == 'L') b.link(d.first, d.second);
-        else if (!parsed.empty()) b.add_parsed_path(parsed[k++]);
-        else b.path(d.first, d.second);
+        if (d.first[0] == 'L') { b.link(d.first, d.second); continue; }
+        const Line& ln = lines[k++];
+        if (!ln.error.empty()) throw Error(ln.error);
+        const size_t start = running;
+        for (size_t i = ln.first_piece; i < ln.first_piece + ln.n_pieces; ++i) {
+            if (!pieces[i].error.empty()) throw Error(pieces[i].error);
+            piece_off[i] = running;
+            running += pieces[i].steps.size();
+        }
+        b.flat.add_path(ln.name.p, ln.name.n, Span{HeapGFAStore::id(start), HeapGFAStore::id(running)}, ln.overlaps);
+    }
+    b.flat.steps.resize(running);
+    {
+        std::atomic<size_t> next{0};
+        auto copy = [&]() {
+            for (size_t i; (i = next.fetch_add(1)) < pieces.size();)
+                if (!pieces[i].steps.empty())
+                    std::memcpy(b.flat.steps.data() + piece_off[i], pieces[i].steps.data(), pieces[i].steps.size() * sizeof(Handle));
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < std::min<size_t>(hw, pieces.size()); ++t) pool.emplace_back(copy);
+        copy();
+        for (auto& t : pool) t.join();
     }
     return std::move(b.flat);
 }

@@ -37,10 +37,11 @@ public:
 // gfaline.rs:201-263: the `1+,23-,4+` step-list state machine.  Returns the number of
 // bytes consumed; emits (name, forward) pairs through `emit`.
 template <typename F>
-size_t parse_steps(const uint8_t* s, size_t n, F&& emit) {
+size_t parse_steps(const uint8_t* s, size_t n, F&& emit, bool* clean_end = nullptr) {
     size_t index = 0;
     bool want_seg = true;
     uint64_t seg = 0;
+    if (clean_end) *clean_end = false;
     while (index < n) {
         const uint8_t byte = s[index++];
         if (want_seg) {
@@ -61,6 +62,9 @@ size_t parse_steps(const uint8_t* s, size_t n, F&& emit) {
             }
         }
     }
+    // clean_end: every byte was consumed without an early stop and the last one completed a step,
+    // i.e. the state is "expecting a comma" -- what a piece cut just before a comma must end in.
+    if (clean_end) *clean_end = !want_seg;
     return index;
 }
 

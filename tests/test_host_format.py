@@ -327,3 +327,54 @@ def test_gfa_text_two_implementations_agree(golden):
     # (print.rs:13-22), so the two letters swap on a round trip.
     q = flatgfa_py.parse_bytes(b"S\t1\tA\nS\t2\tC\nL\t1\t+\t2\t+\t2M1D3I\n")
     assert str(q.links[0]) == "L\t1\t+\t2\t+\t2M1I3D" and q._h.format_gfa().endswith(b"2M1I3D\n")
+
+
+def test_long_step_lists_are_cut_into_pieces_exactly(tmp_path, fgfa_bin):
+    """One path of several MiB of step text is tokenised in pieces by the worker threads; the
+    result (and every failure) must equal the sequential stream parser's (`fgfa < file`), which
+    keeps the reference's one-pass StepsParser (gfaline.rs:201-263)."""
+    rng = np.random.default_rng(5)
+    n_segs = 3000
+    segs = rng.integers(1, n_segs + 1, 1_400_000)
+    toks = [b"%d%s" % (int(x), b"+" if o else b"-") for x, o in zip(segs.tolist(), rng.integers(0, 2, segs.size).tolist())]
+    head = b"H\tVN:Z:1.0\n" + b"".join(b"S\t%d\tAC\n" % i for i in range(1, n_segs + 1))
+
+    def gfa(step_field: bytes, extra=b"") -> bytes:
+        return head + b"L\t1\t+\t2\t-\t3M\n" + b"P\tshort\t1+,2-\t*\n" + b"P\tgiant\t" + step_field + b"\t*\n" + extra
+
+    def both(text: bytes):
+        src = tmp_path / "g.gfa"
+        src.write_bytes(text)
+        a = subprocess.run([fgfa_bin, "-I", str(src), "-o", str(tmp_path / "a.flatgfa")], capture_output=True)
+        b = subprocess.run([fgfa_bin, "-o", str(tmp_path / "b.flatgfa")], input=text, capture_output=True)
+        return a, b
+
+    field = b",".join(toks)
+    assert len(field) > 5 * (1 << 20)                   # at least four pieces
+    a, b = both(gfa(field, b"P\tafter\t3+\t*\n"))
+    assert a.returncode == 0 and b.returncode == 0
+    img = (tmp_path / "a.flatgfa").read_bytes()
+    assert img == (tmp_path / "b.flatgfa").read_bytes()
+    with pb.FlatGFA.load(str(tmp_path / "a.flatgfa")) as g:
+        assert g.path_count == 3 and g.path_step_count(1) == segs.size and g.path_step_count(2) == 1
+        for i in (0, 1, 700_000, segs.size - 1):
+            assert g.step(1, i) == (int(segs[i]) - 1, toks[i].endswith(b"+"))
+    # failures and quirks anywhere in the list behave like the one-pass parser
+    mid = len(toks) // 2
+    variants = {
+        "stray byte mid-list": b",".join(toks[:mid]) + b"x" + b",".join(toks[mid:]),
+        "double sign mid-list": b",".join(toks[:mid]) + b"-," + b",".join(toks[mid:]),
+        "double comma mid-list": b",".join(toks[:mid]) + b",," + b",".join(toks[mid:]),
+        "unknown segment late": b",".join(toks[:-5] + [b"999999+"] + toks[-5:]),
+        "unknown segment before a stray byte": b",".join(toks[:100] + [b"999999+"] + toks[100:mid]) + b"x" + b",".join(toks[mid:]),
+        "trailing number is dropped": field + b",77",
+        "trailing stray byte is swallowed": field + b"x",
+        "trailing comma": field + b",",
+    }
+    for name, f in variants.items():
+        a, b = both(gfa(f))
+        assert a.returncode == b.returncode, name
+        if a.returncode == 0:
+            assert (tmp_path / "a.flatgfa").read_bytes() == (tmp_path / "b.flatgfa").read_bytes(), name
+        else:
+            assert a.stderr == b.stderr and a.stderr, name

@@ -19,7 +19,8 @@ def main():
     runs = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     cfg = synth.CONFIGS[name]
     steps, s, e = synth.make_graph(cfg)
-    path = f"/tmp/synth_{name}.flatgfa"
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    path = os.path.join(ROOT, "build", f"synth_{name}.flatgfa")
     flatgfa_io.write_flatgfa(path, steps, s, e, cfg.n_segs)
     fgfa = os.path.join(ROOT, "bin", "fgfa")
     out = {"config": name, "file_bytes": os.path.getsize(path), "runs": runs}

@@ -10,7 +10,8 @@ from pollen_b200 import synth
 name = sys.argv[1] if len(sys.argv) > 1 else "B"
 cfg = synth.CONFIGS[name]
 steps, s, e = synth.make_graph(cfg)
-src, out = f"/tmp/{name}.gfa", f"/tmp/{name}.flatgfa"
+os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+src, out = os.path.join(ROOT, "build", f"{name}.gfa"), os.path.join(ROOT, "build", f"{name}.flatgfa")
 with open(src, "wb") as f:
     f.write(b"H\tVN:Z:1.0\n")
     f.write(("\n".join(f"S\t{i}\tA" for i in range(1, cfg.n_segs + 1)) + "\n").encode())
