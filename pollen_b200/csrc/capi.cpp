@@ -146,16 +146,9 @@ int flatgfa_format_seg_depth(flatgfa_t gfa, const uint64_t* depth, const uint64_
     if (!gfa || !out || !out_len) return FGFA_ERR_INVALID_ARG;
     const size_t n = gfa->gfa.segs.len();
     if (n && (!depth || !uniq)) return FGFA_ERR_INVALID_ARG;
-    flatgfa::ops::depth::SegDepth t{gfa->gfa, std::vector<uint64_t>(depth, depth + n),
-                                    std::vector<uint64_t>(uniq, uniq + n)};
-    std::string s;
-    t.emit(s);
-    char* buf = static_cast<char*>(std::malloc(s.size() + 1));
+    char* buf = flatgfa::ops::depth::seg_depth_table(gfa->gfa, depth, uniq, out_len);
     if (!buf) return FGFA_ERR_NOMEM;
-    std::memcpy(buf, s.data(), s.size());
-    buf[s.size()] = 0;
     *out = buf;
-    *out_len = s.size();
     return FGFA_OK;
 }
 

@@ -3,9 +3,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -545,29 +547,82 @@ inline char* put_u64(char* p, uint64_t v) {
 }
 }  // namespace
 
-void SegDepth::emit(std::string& out) const {
-    static const char hdr[] = "#node.id\tdepth\tdepth.uniq\n";   // depth.rs:69
-    const size_t n = gfa.segs.len();
-    const size_t base = out.size();
-    out.resize(base + sizeof(hdr) - 1 + n * 54);   // 10 + 20 + 20 digits + 3 separators, worst case
-    char* p = &out[base];
-    std::memcpy(p, hdr, sizeof(hdr) - 1);
-    p += sizeof(hdr) - 1;
-    for (size_t i = 0; i < n; ++i) {               // depth.rs:70-78
+namespace {
+// Rows [lo, hi) of the table into dst (at least (hi - lo) * kRowMax bytes); returns bytes written.
+constexpr size_t kRowMax = 54;   // 10 + 20 + 20 digits + 3 separators, worst case
+size_t format_rows(const FlatGFA& gfa, const uint64_t* depths, const uint64_t* uniq, size_t lo, size_t hi, char* dst) {
+    char* p = dst;
+    for (size_t i = lo; i < hi; ++i) {             // depth.rs:70-78
         p = put_u64(p, (uint32_t)gfa.segs.data[i].name);   // `seg.name as u32`
         *p++ = '\t';
         p = put_u64(p, depths[i]);
         *p++ = '\t';
-        p = put_u64(p, uniq_depths[i]);
+        p = put_u64(p, uniq[i]);
         *p++ = '\n';
     }
-    out.resize((size_t)(p - out.data()));
+    return (size_t)(p - dst);
+}
+
+// The table body as a list of independently formatted blocks, in row order.  Large tables are
+// formatted by a few threads (the reference writes row by row through a locked stdout,
+// emit.rs:13-18; for a 5 M-segment graph the text is ~70 MB).
+struct Block {
+    std::unique_ptr<char[]> data;
+    size_t len = 0;
+};
+std::vector<Block> format_table(const FlatGFA& gfa, const uint64_t* depths, const uint64_t* uniq) {
+    const size_t n = gfa.segs.len();
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const size_t n_blocks = n < (1u << 18) ? 1 : std::min<size_t>(hw * 4, (n + (1u << 16) - 1) >> 16);
+    std::vector<Block> blocks(n_blocks);
+    const size_t per = (n + n_blocks - 1) / std::max<size_t>(n_blocks, 1);
+    auto work = [&](std::atomic<size_t>& next) {
+        for (size_t b; (b = next.fetch_add(1)) < n_blocks;) {
+            const size_t lo = std::min(n, b * per), hi = std::min(n, lo + per);
+            blocks[b].data.reset(new char[std::max<size_t>((hi - lo) * kRowMax, 1)]);
+            blocks[b].len = format_rows(gfa, depths, uniq, lo, hi, blocks[b].data.get());
+        }
+    };
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < std::min<size_t>(hw, n_blocks); ++t) pool.emplace_back([&] { work(next); });
+    work(next);
+    for (auto& t : pool) t.join();
+    return blocks;
+}
+const char kSegDepthHeader[] = "#node.id\tdepth\tdepth.uniq\n";   // depth.rs:69
+}  // namespace
+
+char* seg_depth_table(const FlatGFA& gfa, const uint64_t* depths, const uint64_t* uniq, size_t* len) {
+    const std::vector<Block> blocks = format_table(gfa, depths, uniq);
+    size_t total = sizeof(kSegDepthHeader) - 1;
+    for (const Block& b : blocks) total += b.len;
+    char* buf = static_cast<char*>(std::malloc(total + 1));
+    if (!buf) return nullptr;
+    char* p = buf;
+    std::memcpy(p, kSegDepthHeader, sizeof(kSegDepthHeader) - 1);
+    p += sizeof(kSegDepthHeader) - 1;
+    for (const Block& b : blocks) { std::memcpy(p, b.data.get(), b.len); p += b.len; }
+    *p = 0;
+    *len = total;
+    return buf;
+}
+
+void SegDepth::emit(std::string& out) const {
+    if (depths.size() < gfa.segs.len() || uniq_depths.size() < gfa.segs.len()) throw Error("depth table shorter than the segment pool");
+    const std::vector<Block> blocks = format_table(gfa, depths.data(), uniq_depths.data());
+    size_t total = sizeof(kSegDepthHeader) - 1;
+    for (const Block& b : blocks) total += b.len;
+    out.reserve(out.size() + total);
+    out.append(kSegDepthHeader, sizeof(kSegDepthHeader) - 1);
+    for (const Block& b : blocks) out.append(b.data.get(), b.len);
 }
 
 void SegDepth::emit(FILE* f) const {
-    std::string s;
-    emit(s);
-    std::fwrite(s.data(), 1, s.size(), f);
+    if (depths.size() < gfa.segs.len() || uniq_depths.size() < gfa.segs.len()) throw Error("depth table shorter than the segment pool");
+    const std::vector<Block> blocks = format_table(gfa, depths.data(), uniq_depths.data());
+    std::fwrite(kSegDepthHeader, 1, sizeof(kSegDepthHeader) - 1, f);
+    for (const Block& b : blocks) std::fwrite(b.data.get(), 1, b.len, f);
 }
 
 }  // namespace depth

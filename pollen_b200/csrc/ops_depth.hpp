@@ -35,6 +35,10 @@ struct SegDepth {
     void print() const { emit(stdout); }   // emit.rs:13-18
 };
 
+// The same table for borrowed arrays of gfa.segs.len() entries, in a malloc'ed, NUL-terminated
+// buffer (what the C ABI hands out); nullptr if the allocation fails.
+char* seg_depth_table(const FlatGFA& gfa, const uint64_t* depths, const uint64_t* uniq, size_t* len);
+
 // depth.rs:88-113: node depth over ALL paths, then (length in bp, mean depth) of each
 // queried path.  `paths` are path pool indices (the reference takes an iterator of ids).
 std::pair<std::vector<uint64_t>, std::vector<double>> path_depth(const FlatGFA& gfa,

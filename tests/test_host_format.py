@@ -378,3 +378,19 @@ def test_long_step_lists_are_cut_into_pieces_exactly(tmp_path, fgfa_bin):
             assert (tmp_path / "a.flatgfa").read_bytes() == (tmp_path / "b.flatgfa").read_bytes(), name
         else:
             assert a.stderr == b.stderr and a.stderr, name
+
+
+def test_large_node_depth_table_is_formatted_in_blocks_exactly(tmp_path):
+    """Above 2^18 rows SegDepth::emit formats blocks of rows on several threads; the text must
+    still be the oracle's byte for byte (depth.rs:61-82), including 20-digit counters and names
+    that the `as u32` cast truncates."""
+    n = (1 << 18) + 12_345
+    rng = np.random.default_rng(3)
+    names = rng.integers(1, 1 << 40, n).astype(np.uint64)
+    img = flatgfa_io.build_image(np.zeros(1, np.uint32), [0], [1], n, seg_names=names)
+    f = tmp_path / "wide.flatgfa"
+    img.tofile(str(f))
+    d = rng.integers(0, 1 << 63, n).astype(np.uint64) * np.uint64(2) + np.uint64(1)
+    u = rng.integers(0, 1000, n).astype(np.uint64)
+    with pb.FlatGFA.load(str(f)) as g:
+        assert g.format_seg_depth(d, u) == O.emit(names, d, u)
