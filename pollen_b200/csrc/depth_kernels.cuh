@@ -83,6 +83,55 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t po
 __device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v));
 }
+// Experiment for the next round (tools/ubench.cu built with -DFGFA_DEPTH_PACK=16 or 8; the product
+// builds with 32 and is unchanged): several depth counters per 32-bit word make the adds denser in
+// segment space -- a 32-byte sector then covers 16 or 32 segments instead of 8, and sectors, not
+// lanes, are what the L2 reduction path charges for.  A field that overflows carries into its
+// neighbour, which LOWERS the sum of the decoded fields, so `sum(decoded) == steps added` proves
+// that no field overflowed (tools/experimental_kernels.cuh: k_depth_unpack).
+#ifndef FGFA_DEPTH_PACK
+#define FGFA_DEPTH_PACK 32
+#endif
+__device__ __forceinline__ void depth_add(uint32_t* depth, uint32_t h) {   // h = Handle word, (h >> 1) < n_segs
+#if FGFA_DEPTH_PACK == 32
+    red_add_u32(depth + (h >> 1), 1u);
+#elif FGFA_DEPTH_PACK == 16
+    red_add_u32(depth + (h >> 2), 1u << ((h & 2u) << 3));
+#elif FGFA_DEPTH_PACK == 8
+    red_add_u32(depth + (h >> 3), 1u << ((h & 6u) << 2));
+#else
+#error "FGFA_DEPTH_PACK must be 32, 16 or 8"
+#endif
+}
+#if FGFA_DEPTH_PACK != 32
+// Same experiment, second form (-DFGFA_PACK_MERGE=1): measured without it, the packed adds were
+// SLOWER than one counter per word (0.76 ms with 16-bit fields, 0.94 ms with 8-bit fields against
+// 0.66 ms at config C) although they touch half / a quarter of the sectors -- the lanes of one
+// instruction that hit the same word serialise in the L2 atomic unit.  Here neighbouring lanes that
+// hit the same word are first merged with shuffles (groups of 32/FGFA_DEPTH_PACK lanes inside a run
+// of equal words), so every word is added to by one lane per instruction.  All 32 lanes must call.
+__device__ __forceinline__ void depth_add_merged(uint32_t* depth, uint32_t h, bool valid, uint32_t lane) {
+    constexpr uint32_t kShift = FGFA_DEPTH_PACK == 16 ? 2u : 3u;      // handle -> word index
+    constexpr uint32_t kGroup = 32u / FGFA_DEPTH_PACK;                 // 2 or 4 lanes merge
+    const uint32_t w = valid ? (h >> kShift) : (0xFFFFFFFFu - lane);  // invalid lanes never merge
+    uint32_t v = !valid ? 0u : FGFA_DEPTH_PACK == 16 ? 1u << ((h & 2u) << 3) : 1u << ((h & 6u) << 2);
+    const uint32_t wp = __shfl_up_sync(0xFFFFFFFFu, w, 1);
+    const bool head = lane == 0 || wp != w;
+    const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
+    const uint32_t start = 31u - __clz(heads & (0xFFFFFFFFu >> (31u - lane)));   // head lane of my run
+    const uint32_t off = lane - start;                                 // my position inside the run
+    // level 1: even positions absorb the next lane of the same run
+    uint32_t vn = __shfl_down_sync(0xFFFFFFFFu, v, 1);
+    const bool next_same = lane < 31u && !((heads >> (lane + 1u)) & 1u);
+    if ((off & 1u) == 0u && next_same) v += vn;
+    if (kGroup == 4u) {                                                // level 2: positions 0 mod 4 absorb position +2
+        vn = __shfl_down_sync(0xFFFFFFFFu, v, 2);
+        const bool next2_same = lane < 30u && !((heads >> (lane + 1u)) & 3u);
+        if ((off & 3u) == 0u && next2_same) v += vn;
+    }
+    if (valid && (off & (kGroup - 1u)) == 0u) red_add_u32(depth + w, v);
+}
+#endif
 __device__ __forceinline__ void red_or_b32(uint32_t* p, uint32_t v) {
     asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v));
 }
@@ -353,8 +402,13 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_merged(
             } else {
 #pragma unroll
                 for (int i = 0; i < kItems; ++i) {
-                    if (hh[i] < seg_limit) red_add_u32(depth_ptr + (hh[i] >> 1), 1u);
+#if FGFA_DEPTH_PACK != 32 && defined(FGFA_PACK_MERGE)
+                    depth_add_merged(depth_ptr, hh[i], hh[i] < seg_limit, lane);
+                    if (!WITH_SEEN && hh[i] >= seg_limit && hh[i] != kFiller) *P.err = 1u;
+#else
+                    if (hh[i] < seg_limit) depth_add(depth_ptr, hh[i]);
                     else if (!WITH_SEEN && hh[i] != kFiller) *P.err = 1u;
+#endif
                 }
             }
         }

@@ -344,4 +344,32 @@ __global__ void __launch_bounds__(kThreads, BLOCKS_PER_SM) k_step_stream_warp_ag
     }
 }
 
+// ---------------------------------------------------------------------------
+// Decode of the packed depth counters (-DFGFA_DEPTH_PACK=16|8, see depth_kernels.cuh): adds every
+// field to the u32 depth table, clears the packed word and accumulates the decoded total, which
+// equals the number of steps added iff no field overflowed.
+// ---------------------------------------------------------------------------
+template <int PACK>
+__global__ void __launch_bounds__(256) k_depth_unpack(uint32_t* __restrict__ packed, uint32_t* __restrict__ depth,
+                                                      uint32_t n_segs, unsigned long long* __restrict__ total) {
+    constexpr uint32_t kPer = 32 / PACK;                   // fields per word
+    constexpr uint32_t kMask = PACK == 16 ? 0xFFFFu : 0xFFu;
+    const uint32_t n_words = (n_segs + kPer - 1) / kPer;
+    unsigned long long sum = 0;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+        const uint32_t v = packed[w];
+        if (v == 0) continue;
+        packed[w] = 0;
+#pragma unroll
+        for (uint32_t f = 0; f < kPer; ++f) {
+            const uint32_t c = (v >> (PACK * f)) & kMask;
+            const uint32_t seg = w * kPer + f;
+            if (c && seg < n_segs) { depth[seg] += c; sum += c; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(total, sum);
+}
+
 }  // namespace fgfa

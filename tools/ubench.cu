@@ -323,6 +323,40 @@ int main(int argc, char** argv) {
                    100.0 * alg_bytes / (avg * 1e6) / 6540.2);
         }
     }
+#if FGFA_DEPTH_PACK != 32
+    // packed-counter experiment: memset(packed) + kernel A (packed adds) + kernel B + unpack into a u32 table
+    uint32_t* d_depth32;
+    unsigned long long* d_total;
+    CK(cudaMalloc(&d_depth32, (size_t)cfg.n_segs * 4));
+    CK(cudaMalloc(&d_total, 8));
+    {
+        PopcountParams Qp = Q; Qp.depth = nullptr;
+        const uint32_t n_words_p = (cfg.n_segs + 31) / 32;
+        const int pgrid = (int)((n_words_p + kPopThreads - 1) / kPopThreads);
+        const size_t packed_bytes = ((size_t)cfg.n_segs * FGFA_DEPTH_PACK / 8 + 3) / 4 * 4;
+        float sum = 0, best = 1e30f;
+        for (int r = 0; r < reps + 2; ++r) {
+            CK(cudaMemsetAsync(d_depth, 0, packed_bytes));
+            CK(cudaMemsetAsync(d_total, 0, 8));
+            CK(cudaEventRecord(e0));
+            CK(cudaMemsetAsync(d_depth32, 0, (size_t)cfg.n_segs * 4));
+            k_step_stream_merged<5, kSeenDeferred><<<sms * 10, kThreads, stream_smem_bytes(kSeenDeferred)>>>(S);
+            k_uniq_popcount<4><<<pgrid, kPopThreads>>>(Qp);
+            k_depth_unpack<FGFA_DEPTH_PACK><<<sms * 8, 256>>>(d_depth, d_depth32, cfg.n_segs, d_total);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (r >= 2) { best = std::min(best, ms); sum += ms; }
+        }
+        unsigned long long total = 0;
+        CK(cudaMemcpy(&total, d_total, 8, cudaMemcpyDeviceToHost));
+        printf("PACKED%d PIPELINE memset+A+B+unpack  best %8.3f ms  avg %8.3f ms   decoded total %llu vs %llu steps: %s\n",
+               FGFA_DEPTH_PACK, best, sum / reps, total, (unsigned long long)cfg.n_steps,
+               total == cfg.n_steps ? "no field overflowed" : "OVERFLOW (fall back to 32-bit counters)");
+        CK(cudaMemcpy(d_depth, d_depth32, (size_t)cfg.n_segs * 4, cudaMemcpyDeviceToDevice));   // verified below
+    }
+#endif
     CK(cudaDeviceSynchronize());
     uint32_t err;
     CK(cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));
@@ -340,7 +374,9 @@ int main(int argc, char** argv) {
                                             cfg.n_segs, o_depth.data(), o_uniq.data());
         auto c1 = std::chrono::steady_clock::now();
         double cs = std::chrono::duration<double>(c1 - c0).count();
-        uint64_t bad = 0, sum_d = 0, sum_u = 0;
+        uint64_t bad = 0, sum_d = 0, sum_u = 0, max_d = 0;
+        for (uint32_t i = 0; i < cfg.n_segs; ++i) max_d = std::max<uint64_t>(max_d, o_depth[i]);
+        printf("max depth of a segment = %llu\n", (unsigned long long)max_d);
         for (uint32_t i = 0; i < cfg.n_segs; ++i) {
             bad += (g_depth[i] != o_depth[i]) + (g_uniq[i] != o_uniq[i]);
             sum_d += o_depth[i]; sum_u += o_uniq[i];
