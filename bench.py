@@ -14,7 +14,8 @@ graph is sharded by whole paths (configs[3]), so scaling is "strong".
             H2D -> kernels (-> allreduce) -> D2H of depth/uniq, every step.
 `roofline`  algorithmic bytes of kernel A / its CUDA-event duration inside the timed
             region, against MEASURED_PEAKS.json's HBM copy bandwidth.
-`cpu_baseline`  the oracle (C port of depth.rs:15-39, single thread like the reference)
+`cpu_baseline`  the oracle (C port of depth.rs:15-39, single thread like the reference); its
+                `path_parallel_variant` is a multi-threaded CPU figure that is NOT the reference's algorithm
             timed on this box, rank 0, N = 1 only.
 `--impl reference` times that CPU port alone (the Rust reference cannot be built here).
 """
@@ -96,6 +97,27 @@ def time_oracle(cfg, steps, start, end, reps):
     return best
 
 
+def time_parallel_variant(cfg, steps, start, end, reps=2):
+    """The path-parallel CPU variant (oracle_seg_depth_with_uniq_parallel), reported BESIDE the
+    baseline: it is not the reference's algorithm (depth.rs:15-39 is single-threaded), SURVEY 8d
+    asks for it as an optional, fairer CPU figure.  Never raises: the baseline proper does not depend on it."""
+    try:
+        import oracle_lib as O
+        threads = max(1, min(os.cpu_count() or 1, 64, cfg.n_paths))
+        best = 0.0
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            rc, d, u = O.depth_with_uniq_parallel(steps, start, end, cfg.n_segs, threads)
+            dt = time.perf_counter() - t0
+            if rc != 0:
+                return None
+            best = max(best, cfg.n_steps / dt)
+        return {"value": best, "unit": UNIT, "threads": threads,
+                "note": "whole paths per thread, private counters + reduction; NOT the reference's algorithm"}
+    except Exception as exc:   # noqa: BLE001
+        return {"unavailable": type(exc).__name__}
+
+
 def run_reference(args, cfg, rank):
     """--impl reference: the reference's algorithm on the host CPU.  The Rust crate cannot
     be built here (no cargo, crates not vendored), so this is the oracle port of
@@ -122,7 +144,8 @@ def run_reference(args, cfg, rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(cfg, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count()},
+                         "host_cores": os.cpu_count(),
+                         "path_parallel_variant": time_parallel_variant(cfg, steps, start, end)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -370,7 +393,8 @@ def main():
         v = time_oracle(cfg, h_steps_np, ls, le, reps=3)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"full config {cfg.name} ({cfg.n_steps} steps), best of 3 passes of the single-threaded oracle",
-               "host_cores": os.cpu_count()}
+               "host_cores": os.cpu_count(),
+               "path_parallel_variant": time_parallel_variant(cfg, h_steps_np, ls, le)}
 
     if rank == 0:
         print(json.dumps({

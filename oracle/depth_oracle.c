@@ -348,3 +348,105 @@ int64_t oracle_emit_interval_depth(const uint8_t* names, const uint64_t* name_of
     }
     return (int64_t)w;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * A path-parallel CPU variant, reported BESIDE the baseline and labelled as such: it is NOT
+ * the reference's algorithm (depth.rs:15-39 is one thread sharing one `seen` bitmap across
+ * paths).  SURVEY §8d asks for it as an optional fairer CPU number: every thread takes whole
+ * paths from a shared counter (longest first), counts into private u32 arrays with a private
+ * bitmap, and the private arrays are summed per segment slice at the end.  Same results as
+ * oracle_seg_depth_with_uniq (checked in tests/test_oracle_golden.py).
+ * ------------------------------------------------------------------------------------------ */
+#include <pthread.h>
+
+typedef struct {
+    const uint32_t* steps;
+    uint64_t n_steps;
+    const uint32_t* spans;
+    const uint32_t* order;       /* path indices, longest first */
+    uint32_t n_paths, n_segs, n_threads, tid;
+    volatile uint32_t* next;     /* shared work counter */
+    uint32_t* depth32;           /* [n_threads][n_segs] */
+    uint32_t* uniq32;
+    uint64_t* depth;             /* outputs */
+    uint64_t* uniq;
+    pthread_barrier_t* barrier;
+    volatile int* failed;
+} mt_arg_t;
+
+static void* mt_worker(void* p) {
+    mt_arg_t* a = (mt_arg_t*)p;
+    uint32_t* d = a->depth32 + (size_t)a->tid * a->n_segs;
+    uint32_t* u = a->uniq32 + (size_t)a->tid * a->n_segs;
+    size_t words = ((size_t)a->n_segs + 63) / 64;
+    uint64_t* seen = (uint64_t*)calloc(words ? words : 1, 8);
+    if (!seen) *a->failed = -2;
+    for (;;) {
+        uint32_t k = __atomic_fetch_add(a->next, 1u, __ATOMIC_RELAXED);
+        if (k >= a->n_paths || *a->failed) break;
+        uint32_t path = a->order[k];
+        uint32_t s = a->spans[2 * path], e = a->spans[2 * path + 1];
+        if (s > e || e > a->n_steps) { *a->failed = -1; break; }
+        memset(seen, 0, words * 8);
+        for (uint32_t i = s; i < e; ++i) {
+            uint32_t seg = handle_segment(a->steps[i]);
+            if (seg >= a->n_segs) { *a->failed = -1; break; }
+            d[seg] += 1;
+            uint64_t bit = 1ull << (seg & 63);
+            if (!(seen[seg >> 6] & bit)) { seen[seg >> 6] |= bit; u[seg] += 1; }
+        }
+    }
+    free(seen);
+    pthread_barrier_wait(a->barrier);
+    /* reduction: this thread's slice of the segment axis */
+    size_t lo = (size_t)a->n_segs * a->tid / a->n_threads, hi = (size_t)a->n_segs * (a->tid + 1) / a->n_threads;
+    for (size_t i = lo; i < hi; ++i) {
+        uint64_t sd = 0, su = 0;
+        for (uint32_t t = 0; t < a->n_threads; ++t) {
+            sd += a->depth32[(size_t)t * a->n_segs + i];
+            su += a->uniq32[(size_t)t * a->n_segs + i];
+        }
+        a->depth[i] = sd;
+        a->uniq[i] = su;
+    }
+    return NULL;
+}
+
+static const uint32_t* g_sort_spans;
+static int by_length_desc(const void* x, const void* y) {
+    uint32_t a = *(const uint32_t*)x, b = *(const uint32_t*)y;
+    uint32_t la = g_sort_spans[2 * a + 1] - g_sort_spans[2 * a], lb = g_sort_spans[2 * b + 1] - g_sort_spans[2 * b];
+    return la < lb ? 1 : la > lb ? -1 : (a > b) - (a < b);
+}
+
+int oracle_seg_depth_with_uniq_parallel(const uint32_t* steps, uint64_t n_steps, const uint32_t* spans,
+                                        uint32_t n_paths, uint32_t n_segs, uint64_t* depth, uint64_t* uniq,
+                                        uint32_t n_threads) {
+    if (n_threads == 0) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    for (uint32_t p = 0; p < n_paths; ++p)
+        if (spans[2 * p] > spans[2 * p + 1] || spans[2 * p + 1] > n_steps) return -1;
+    size_t cells = (size_t)n_threads * (n_segs ? n_segs : 1);
+    uint32_t* d32 = (uint32_t*)calloc(cells, 4);
+    uint32_t* u32 = (uint32_t*)calloc(cells, 4);
+    uint32_t* order = (uint32_t*)malloc((size_t)(n_paths ? n_paths : 1) * 4);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
+    mt_arg_t* args = (mt_arg_t*)malloc(sizeof(mt_arg_t) * n_threads);
+    if (!d32 || !u32 || !order || !th || !args) { free(d32); free(u32); free(order); free(th); free(args); return -2; }
+    for (uint32_t p = 0; p < n_paths; ++p) order[p] = p;
+    g_sort_spans = spans;
+    qsort(order, n_paths, 4, by_length_desc);
+    pthread_barrier_t barrier;
+    pthread_barrier_init(&barrier, NULL, n_threads);
+    volatile uint32_t next = 0;
+    volatile int failed = 0;
+    for (uint32_t t = 0; t < n_threads; ++t) {
+        mt_arg_t a = {steps, n_steps, spans, order, n_paths, n_segs, n_threads, t, &next, d32, u32, depth, uniq, &barrier, &failed};
+        args[t] = a;
+        pthread_create(&th[t], NULL, mt_worker, &args[t]);
+    }
+    for (uint32_t t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    pthread_barrier_destroy(&barrier);
+    free(d32); free(u32); free(order); free(th); free(args);
+    return failed;
+}

@@ -17,6 +17,8 @@ def oracle():
         h = C.CDLL(path)
         h.oracle_seg_depth_with_uniq.restype = C.c_int
         h.oracle_seg_depth_with_uniq.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        h.oracle_seg_depth_with_uniq_parallel.restype = C.c_int
+        h.oracle_seg_depth_with_uniq_parallel.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
         h.oracle_seg_depth.restype = C.c_int
         h.oracle_seg_depth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         h.oracle_file_seg_depth_with_uniq.restype = C.c_int
@@ -70,6 +72,17 @@ def depth_with_uniq(steps, start, end, n_segs):
     d = np.empty(n_segs, dtype=np.uint64)
     u = np.empty(n_segs, dtype=np.uint64)
     rc = oracle().oracle_seg_depth_with_uniq(steps.ctypes.data, steps.size, sp.ctypes.data, len(start), n_segs, d.ctypes.data, u.ctypes.data)
+    return rc, d, u
+
+
+def depth_with_uniq_parallel(steps, start, end, n_segs, n_threads):
+    """The path-parallel CPU variant (NOT the reference's algorithm; reported beside the baseline)."""
+    steps = np.ascontiguousarray(steps, dtype=np.uint32)
+    sp = spans_of(start, end)
+    d = np.empty(n_segs, dtype=np.uint64)
+    u = np.empty(n_segs, dtype=np.uint64)
+    rc = oracle().oracle_seg_depth_with_uniq_parallel(steps.ctypes.data, steps.size, sp.ctypes.data, len(start), n_segs,
+                                                       d.ctypes.data, u.ctypes.data, n_threads)
     return rc, d, u
 
 

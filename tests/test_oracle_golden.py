@@ -93,3 +93,19 @@ def test_oracle_empty_inputs():
     assert rc == 0 and d.size == 0
     rc, d, u = O.depth_with_uniq(np.zeros(0, np.uint32), [0, 0], [0, 0], 3)
     assert rc == 0 and not d.any() and not u.any()
+
+
+def test_path_parallel_variant_equals_the_oracle():
+    """The multi-threaded CPU variant bench.py reports beside the baseline gives the oracle's results."""
+    from pollen_b200 import synth
+    for name in ("tiny", "tinyE"):
+        cfg = synth.CONFIGS[name]
+        steps, s, e = synth.make_graph(cfg)
+        rc, d, u = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+        for threads in (1, 3, 8):
+            rc2, d2, u2 = O.depth_with_uniq_parallel(steps, s, e, cfg.n_segs, threads)
+            assert rc == 0 and rc2 == 0 and (d == d2).all() and (u == u2).all()
+    rc, _, _ = O.depth_with_uniq_parallel(np.array([0, 9], np.uint32), [0], [2], 3, 4)
+    assert rc == -1                                        # segment id out of range
+    rc, d, u = O.depth_with_uniq_parallel(np.zeros(0, np.uint32), [], [], 5, 4)
+    assert rc == 0 and not d.any() and not u.any()
