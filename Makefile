@@ -65,7 +65,15 @@ build/ubench: tools/ubench.cu tools/experimental_kernels.cuh $(CSRC)/depth_kerne
 	$(CXX) -O3 -std=c++17 -c $(CSRC)/synth.cpp -o build/synth.o
 	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench.cu build/depth_oracle.o build/synth.o -o $@
 
+# kernel-A variants for tools/ubench.cu (not part of `all`): packed depth counters, with and without
+# the in-warp merge of same-word lanes; steps-per-thread.  See DESIGN.md section 5.
+experiments: build/ubench
+	for v in 16 8; do \
+	  $(NVCC) -DFGFA_DEPTH_PACK=$$v $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench.cu build/depth_oracle.o build/synth.o -o build/ubench_p$$v; \
+	  $(NVCC) -DFGFA_DEPTH_PACK=$$v -DFGFA_PACK_MERGE=1 $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench.cu build/depth_oracle.o build/synth.o -o build/ubench_p$${v}m; \
+	done
+
 clean:
 	rm -rf build bin $(LIBDIR)/*.so $(LIBDIR)/*.a oracle/*.so
 
-.PHONY: all oracle tools clean
+.PHONY: all oracle tools clean experiments
