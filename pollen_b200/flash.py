@@ -668,19 +668,24 @@ def main(argv: Optional[List[str]] = None) -> int:    # main.rs:38-54
     if cmd is None and script is not None:
         with open(script, encoding="utf-8") as f:
             cmd = f.read()
-    if cmd is not None:
-        out = run_shell(cmd, pretend, optimize_ir)
+    def once(text: str) -> int:
+        try:
+            out = run_shell(text, pretend, optimize_ir)
+        except (Unsupported, ValueError, OSError, RuntimeError) as exc:   # the reference panics here
+            print(f"flash: {type(exc).__name__}: {exc}", file=sys.stderr)
+            return 1
         if out is not None:
             sys.stdout.write(out)
         return 0
+
+    if cmd is not None:
+        return once(cmd)
     while True:                                        # the interactive prompt, main.rs:22-36
         try:
             line = input("$ ")
         except (EOFError, KeyboardInterrupt):
             return 0
-        out = run_shell(line, pretend, optimize_ir)
-        if out is not None:
-            sys.stdout.write(out)
+        once(line)
 
 
 if __name__ == "__main__":
