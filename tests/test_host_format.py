@@ -394,3 +394,55 @@ def test_large_node_depth_table_is_formatted_in_blocks_exactly(tmp_path):
     u = rng.integers(0, 1000, n).astype(np.uint64)
     with pb.FlatGFA.load(str(f)) as g:
         assert g.format_seg_depth(d, u) == O.emit(names, d, u)
+
+
+def test_random_gfa_round_trips_through_both_writers():
+    """Property test (hypothesis): any well-formed GFA of H/S/L/P lines -- arbitrary line order,
+    non-sequential names, optional fields, CIGAR overlaps on links and paths -- survives
+    text -> FlatGFA -> text and text -> .flatgfa image -> text unchanged (tests/turnt.toml:162-172)."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    from pollen_b200 import flatgfa_py
+
+    # CIGAR lengths above 255 are rejected by the reference itself (flatgfa.rs:231 "length too large")
+    cigar = st.lists(st.tuples(st.integers(0, 255), st.sampled_from("MN")), min_size=1, max_size=3).map(
+        lambda ops: "".join(f"{n}{c}" for n, c in ops))
+
+    @st.composite
+    def graphs(draw):
+        n = draw(st.integers(1, 12))
+        names = draw(st.lists(st.integers(1, 5000), min_size=n, max_size=n, unique=True))
+        lines = []
+        for nm in names:
+            seq = draw(st.text("ACGTN", min_size=1, max_size=12))
+            opt = draw(st.sampled_from(["", "\tLN:i:%d" % len(seq), "\tRC:i:7\txx:Z:a b"]))
+            lines.append(("S", f"S\t{nm}\t{seq}{opt}"))
+        handle = st.tuples(st.sampled_from(names), st.sampled_from("+-"))
+        for _ in range(draw(st.integers(0, 8))):
+            (a, ao), (b, bo) = draw(handle), draw(handle)
+            lines.append(("L", f"L\t{a}\t{ao}\t{b}\t{bo}\t{draw(cigar)}"))
+        for k in range(draw(st.integers(0, 5))):
+            steps = draw(st.lists(handle, min_size=1, max_size=15))
+            ov = draw(st.one_of(st.just("*"), st.lists(cigar, min_size=1, max_size=3).map(",".join)))
+            lines.append(("P", f"P\tp{k}#x\t" + ",".join(f"{s}{o}" for s, o in steps) + f"\t{ov}"))
+        # links and paths may come before the segments they name (parse.rs:83-91 defers them)
+        order = draw(st.permutations(range(len(lines))))
+        body = [lines[i][1] for i in order]
+        if draw(st.booleans()):
+            body.insert(draw(st.integers(0, len(body))), "H\tVN:Z:1.0")
+        return "\n".join(body) + "\n"
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(graphs())
+    def check(text):
+        g = flatgfa_py.parse_bytes(text.encode())
+        assert g._h.format_gfa().decode() == text          # C++ printer
+        assert str(g) == text                              # Python front end
+        img = g._h.image()
+        assert str(flatgfa_py.FlatGFA(g._h, img)) == text  # through the .flatgfa image
+
+    check()
+    with pytest.raises(pb.DepthError):                     # the limit itself
+        pb.FlatGFA.parse_bytes(b"S\t1\tA\nL\t1\t+\t1\t+\t256M\n")
+    assert pb.FlatGFA.parse_bytes(b"S\t1\tA\nL\t1\t+\t1\t+\t255M\n").format_gfa().endswith(b"255M\n")
