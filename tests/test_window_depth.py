@@ -278,3 +278,25 @@ def test_gpu_window_depth_errors(fgfa_bin, tmp_path):
     with pytest.raises(pb.DepthError):
         pb.window_depth_steps(steps, [0], [3], [1, 1, 1], 1, 4)    # path index out of range
     assert pb.interval_depth_steps(steps, [0], [3], [1, 1, 1], 0, [], []).size == 0
+
+
+def test_bed_parsers_agree_on_arbitrary_bytes():
+    """Property test: the product's BEDParser (C++) and the oracle's restatement (C) accept and
+    reject the same inputs and produce the same entries, whatever the bytes (flatbed.rs:126-152)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    line = st.text(alphabet="\t 0123456789xy#-+.", min_size=0, max_size=14).map(lambda s: s.encode())
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.lists(line, min_size=0, max_size=6), st.booleans())
+    def check(lines, terminated):
+        text = b"\n".join(lines) + (b"\n" if terminated and lines else b"")
+        want = O.parse_bed(text)
+        if want is None:
+            with pytest.raises(pb.DepthError):
+                pb.FlatBED.parse(text)
+        else:
+            assert pb.FlatBED.parse(text).entries() == want
+
+    check()
