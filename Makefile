@@ -73,7 +73,15 @@ experiments: build/ubench
 	  $(NVCC) -DFGFA_DEPTH_PACK=$$v -DFGFA_PACK_MERGE=1 $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench.cu build/depth_oracle.o build/synth.o -o build/ubench_p$${v}m; \
 	done
 
+# host code with AddressSanitizer + UndefinedBehaviorSanitizer (system g++ so that the runtime matches
+# libasan.so.8); the CUDA objects are linked as they are.  Used by tools/asan_host.sh.
+ASAN_SRCS := ops_depth ops_window_depth flatbed file parse print capi
+asan: $(LIBDIR)/libflatgfa.so
+	@mkdir -p build/asan
+	for f in $(ASAN_SRCS); do /usr/bin/g++ -O1 -g -std=c++17 -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -I/usr/local/cuda/include -c $(CSRC)/$$f.cpp -o build/asan/$$f.o || exit 1; done
+	$(NVCC) -ccbin /usr/bin/g++ $(ARCH) -shared -o build/asan/libflatgfa_asan.so $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(addprefix build/asan/,$(addsuffix .o,$(ASAN_SRCS))) -cudart static -lpthread -Xlinker /usr/lib/x86_64-linux-gnu/libasan.so.8 -Xlinker /usr/lib/x86_64-linux-gnu/libubsan.so.1
+
 clean:
 	rm -rf build bin $(LIBDIR)/*.so $(LIBDIR)/*.a oracle/*.so
 
-.PHONY: all oracle tools clean experiments
+.PHONY: all oracle tools clean experiments asan
