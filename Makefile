@@ -81,7 +81,14 @@ asan: $(LIBDIR)/libflatgfa.so
 	for f in $(ASAN_SRCS); do /usr/bin/g++ -O1 -g -std=c++17 -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -I/usr/local/cuda/include -c $(CSRC)/$$f.cpp -o build/asan/$$f.o || exit 1; done
 	$(NVCC) -ccbin /usr/bin/g++ $(ARCH) -shared -o build/asan/libflatgfa_asan.so $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(addprefix build/asan/,$(addsuffix .o,$(ASAN_SRCS))) -cudart static -lpthread -Xlinker /usr/lib/x86_64-linux-gnu/libasan.so.8 -Xlinker /usr/lib/x86_64-linux-gnu/libubsan.so.1
 
+TSAN_SRCS := ops_depth ops_window_depth flatbed file parse print
+tsan: $(LIBDIR)/libflatgfa.so
+	@mkdir -p build/tsan
+	for f in $(TSAN_SRCS); do /usr/bin/g++ -O1 -g -std=c++17 -fPIC -fsanitize=thread -I/usr/local/cuda/include -c $(CSRC)/$$f.cpp -o build/tsan/$$f.o || exit 1; done
+	/usr/bin/g++ -O1 -g -std=c++17 -fsanitize=thread -I/usr/local/cuda/include -c tools/tsan_host.cpp -o build/tsan/main.o
+	$(NVCC) -ccbin /usr/bin/g++ $(ARCH) -o build/tsan/tsan_host build/tsan/main.o $(addprefix build/tsan/,$(addsuffix .o,$(TSAN_SRCS))) $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o -cudart static -lpthread -Xlinker -ltsan
+
 clean:
 	rm -rf build bin $(LIBDIR)/*.so $(LIBDIR)/*.a oracle/*.so
 
-.PHONY: all oracle tools clean experiments asan
+.PHONY: all oracle tools clean experiments asan tsan
