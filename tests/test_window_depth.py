@@ -288,7 +288,7 @@ def test_bed_parsers_agree_on_arbitrary_bytes():
 
     line = st.text(alphabet="\t 0123456789xy#-+.", min_size=0, max_size=14).map(lambda s: s.encode())
 
-    @settings(max_examples=400, deadline=None)
+    @settings(max_examples=400, deadline=None, derandomize=True)
     @given(st.lists(line, min_size=0, max_size=6), st.booleans())
     def check(lines, terminated):
         text = b"\n".join(lines) + (b"\n" if terminated and lines else b"")
