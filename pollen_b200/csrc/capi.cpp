@@ -34,6 +34,23 @@ flatgfa_string_t to_string(flatgfa::Pool<uint8_t> p) {
 }
 }  // namespace
 
+namespace {
+int text_out(const std::string& s, char** out, size_t* out_len) {
+    char* buf = static_cast<char*>(std::malloc(s.size() + 1));
+    if (!buf) return FGFA_ERR_NOMEM;
+    std::memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+    *out = buf;
+    *out_len = s.size();
+    return FGFA_OK;
+}
+int code_of(const std::exception& e) {
+    g_err = e.what();
+    if (std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "no usable CUDA device")) return FGFA_ERR_NO_DEVICE;
+    return FGFA_ERR_INVALID_ARG;
+}
+}  // namespace
+
 extern "C" {
 
 const char* flatgfa_last_error(void) { return g_err.c_str(); }
@@ -195,23 +212,6 @@ int flatgfa_format_path_depth(flatgfa_t gfa, const uint32_t* path_ids, uint32_t 
     *out_len = s.size();
     return FGFA_OK;
 }
-
-namespace {
-int text_out(const std::string& s, char** out, size_t* out_len) {
-    char* buf = static_cast<char*>(std::malloc(s.size() + 1));
-    if (!buf) return FGFA_ERR_NOMEM;
-    std::memcpy(buf, s.data(), s.size());
-    buf[s.size()] = 0;
-    *out = buf;
-    *out_len = s.size();
-    return FGFA_OK;
-}
-int code_of(const std::exception& e) {
-    g_err = e.what();
-    if (std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "no usable CUDA device")) return FGFA_ERR_NO_DEVICE;
-    return FGFA_ERR_INVALID_ARG;
-}
-}  // namespace
 
 flatbed_t flatbed_parse_mem(const uint8_t* bed_text, size_t bed_len) {
     if (bed_len && !bed_text) { g_err = "null text"; return nullptr; }
