@@ -9,6 +9,7 @@
 //   fgfa [-i FLATGFA | -I GFA | < GFA] window-depth PATH SIZE   (cmds.rs:477-496)
 //   fgfa [-i FLATGFA | -I GFA | < GFA] -o OUT.flatgfa    convert to the binary format
 //   fgfa [-i FLATGFA | -I GFA | < GFA] [-O OUT.gfa]      GFA text to a file or stdout (print.rs)
+//   fgfa -m [-p N] -o OUT.flatgfa [-I GFA | < GFA]       preallocated translation (main.rs:216-248)
 // The other subcommands of the reference are outside this repository's scope
 // and are rejected with an error.
 #include <cstdio>
@@ -92,9 +93,29 @@ int main(int argc, char** argv) {
                      a.command.c_str());
         return 1;
     }
-    if (a.mutate) {
-        std::fprintf(stderr, "fgfa: in-place mutation (-m) is outside the scope of this build\n");
-        return 1;
+    // -m (cli/main.rs:59-65, 216-248): with only an output file it is the "preallocated" translation --
+    // the GFA is parsed into a file whose pools have spare capacity (estimated from the text, or guessed
+    // from -p when reading stdin).  With -i the file is opened for mutation in the reference; no command
+    // of this build mutates, so it is simply viewed.
+    if (a.mutate && a.command.empty() && a.input.empty() && !a.output.empty()) {
+        try {
+            flatgfa::HeapGFAStore store;
+            flatgfa::file::Toc caps;
+            if (!a.input_gfa.empty()) {
+                flatgfa::MappedFile text(a.input_gfa);
+                caps = flatgfa::estimate_toc(text.data(), text.size());
+                store = flatgfa::Parser::parse_mem(text.data(), text.size());
+            } else {
+                caps = flatgfa::file::Toc::guess(a.prealloc_factor);
+                store = flatgfa::Parser::parse_stream(stdin);
+            }
+            const std::vector<uint8_t> img = flatgfa::file::dump_preallocated(store.view(), caps);
+            flatgfa::write_file(a.output, img.data(), img.size());
+            return 0;
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "Error: %s\n", e.what());
+            return 1;
+        }
     }
 
     try {

@@ -114,6 +114,73 @@ void dump_impl(const FlatGFA& g, uint8_t* buf, size_t slack) {
 
 void dump(const FlatGFA& g, uint8_t* buf) { dump_impl(g, buf, 0); }
 
+Toc Toc::guess(size_t f) {
+    Toc t;
+    t.magic = MAGIC_NUMBER;
+    auto empty = [](size_t cap) { return Size{0, (uint64_t)cap}; };
+    t.header = empty(128);
+    t.segs = empty(32 * f * f);
+    t.paths = empty(f);
+    t.links = empty(32 * f * f);
+    t.steps = empty(1024 * f * f);
+    t.seq_data = empty(512 * f * f);
+    t.overlaps = empty(256 * f);
+    t.alignment = empty(64 * f * f);
+    t.name_data = empty(64 * f);
+    t.optional_data = empty(512 * f * f);
+    t.line_order = empty(64 * f * f);
+    return t;
+}
+
+Toc Toc::estimate(size_t segs, size_t links, size_t paths, size_t header_bytes, size_t seg_bytes, size_t path_bytes) {
+    Toc t;
+    t.magic = MAGIC_NUMBER;
+    auto empty = [](size_t cap) { return Size{0, (uint64_t)cap}; };
+    t.header = empty(header_bytes);
+    t.segs = empty(segs);
+    t.paths = empty(paths);
+    t.links = empty(links);
+    t.steps = empty(path_bytes / 3);
+    t.seq_data = empty(seg_bytes);
+    t.overlaps = empty((links + paths) * 2);
+    t.alignment = empty(links * 2 + paths * 4);
+    t.name_data = empty(paths * 512);
+    t.optional_data = empty(links * 16);
+    t.line_order = empty(segs + links + paths + 8);
+    return t;
+}
+
+namespace {
+template <typename T>
+uint8_t* put_cap(uint8_t* p, const Pool<T>& pool, Size& sz) {
+    if (pool.len() > sz.capacity) throw Error("capacity overflow");   // tinyvec SliceVec::push in the reference
+    sz.len = pool.len();
+    const size_t n = pool.len() * sizeof(T);
+    if (n) std::memcpy(p, pool.data, n);
+    return p + (size_t)sz.capacity * sizeof(T);                        // the rest of the slots stay zero
+}
+}  // namespace
+
+std::vector<uint8_t> dump_preallocated(const FlatGFA& g, const Toc& capacities) {
+    Toc toc = capacities;
+    toc.magic = MAGIC_NUMBER;
+    std::vector<uint8_t> out(toc.size(), 0);
+    uint8_t* p = out.data() + sizeof(Toc);
+    p = put_cap(p, g.header, toc.header);
+    p = put_cap(p, g.segs, toc.segs);
+    p = put_cap(p, g.paths, toc.paths);
+    p = put_cap(p, g.links, toc.links);
+    p = put_cap(p, g.steps, toc.steps);
+    p = put_cap(p, g.seq_data, toc.seq_data);
+    p = put_cap(p, g.overlaps, toc.overlaps);
+    p = put_cap(p, g.alignment, toc.alignment);
+    p = put_cap(p, g.name_data, toc.name_data);
+    p = put_cap(p, g.optional_data, toc.optional_data);
+    put_cap(p, g.line_order, toc.line_order);
+    std::memcpy(out.data(), &toc, sizeof(Toc));                        // file.rs: Toc::for_fixed_store
+    return out;
+}
+
 std::vector<uint8_t> dump_with_slack(const FlatGFA& g, size_t extra) {
     Toc toc = Toc::full(g);
     Size* s = const_cast<Size*>(sizes_of(toc));

@@ -25,6 +25,10 @@ struct Toc {             // file.rs:11-27
         optional_data, line_order;
     size_t size() const;                 // file.rs:64-79: total file size in bytes
     static Toc full(const FlatGFA& g);   // file.rs:82-97: capacity == len everywhere
+    static Toc guess(size_t factor);     // file.rs:117-132: capacities of a fresh file, all pools empty
+    // file.rs:136-158: capacities estimated from measurements of the GFA text
+    static Toc estimate(size_t segs, size_t links, size_t paths, size_t header_bytes, size_t seg_bytes,
+                        size_t path_bytes);
 };
 #pragma pack(pop)
 static_assert(sizeof(Toc) == 184, "Toc is 8 + 11*16 bytes");
@@ -42,6 +46,11 @@ void dump(const FlatGFA& g, uint8_t* buf);     // file.rs:290-307; buf must hold
 // A compact image with `capacity` slack on chosen pools, as the reference's
 // preallocated in-place files have (file.rs:117-158): used to test capacity > len.
 std::vector<uint8_t> dump_with_slack(const FlatGFA& g, size_t extra_per_pool);
+// The image a graph has after being parsed INTO a preallocated file (file.rs:261-272 `init` +
+// `Parser::for_slice`, cli/main.rs:216-248 `prealloc_translate`): pool i occupies capacities.<i>.capacity
+// slots, of which the first len hold the graph and the rest are zero.  Throws "capacity overflow" where
+// the reference's fixed-size store would (a pool larger than its capacity).
+std::vector<uint8_t> dump_preallocated(const FlatGFA& g, const Toc& capacities);
 
 }  // namespace file
 

@@ -400,6 +400,27 @@ static bool gpu_paths(Builder& b, const uint8_t* buf, size_t len,
     return true;
 }
 
+file::Toc estimate_toc(const uint8_t* buf, size_t len) {
+    size_t segs = 0, links = 0, paths = 0, header_bytes = 0, seg_bytes = 0, path_bytes = 0;
+    size_t pos = 0;
+    while (pos < len) {
+        const uint8_t marker = buf[pos];
+        const void* nl = std::memchr(buf + pos, '\n', len - pos);
+        const size_t rest = len - pos;
+        const size_t next = nl ? (size_t)((const uint8_t*)nl - (buf + pos)) : rest + 1;   // parse.rs:187
+        switch (marker) {
+            case 'H': header_bytes += next; break;
+            case 'S': ++segs; seg_bytes += next; break;
+            case 'L': ++links; break;
+            case 'P': ++paths; path_bytes += next; break;
+            default: throw Error("unknown line type");
+        }
+        if (next >= rest) break;
+        pos += next + 1;
+    }
+    return file::Toc::estimate(segs, links, paths, header_bytes, seg_bytes, path_bytes);
+}
+
 HeapGFAStore Parser::parse_stream(FILE* in) {
     Builder b;
     std::vector<std::string> links, paths;

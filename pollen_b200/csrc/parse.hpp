@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <unordered_map>
 
+#include "file.hpp"
 #include "flatgfa.hpp"
 
 namespace flatgfa {
@@ -33,6 +34,11 @@ public:
     // even without a trailing newline (BufRead::split).
     static HeapGFAStore parse_stream(FILE* in);
 };
+
+// parse.rs:176-216: one scan over GFA text counting the lines of each kind and the bytes of the H, S and
+// P lines, turned into the capacities of a preallocated file by Toc::estimate.  Throws on a line that
+// does not start with H, S, L or P (the reference panics with "unknown line type").
+file::Toc estimate_toc(const uint8_t* buf, size_t len);
 
 // gfaline.rs:201-263: the `1+,23-,4+` step-list state machine.  Returns the number of
 // bytes consumed; emits (name, forward) pairs through `emit`.

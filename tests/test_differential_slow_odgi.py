@@ -92,3 +92,5 @@ def test_every_reference_gfa_fixture_round_trips(tmp_path):
         flat = str(tmp_path / "t.flatgfa")
         subprocess.run([fgfa, "-I", f, "-o", flat], check=True)
         assert subprocess.run([fgfa, "-i", flat], capture_output=True, check=True).stdout == want, f
+        subprocess.run([fgfa, "-m", "-p", "128", "-o", flat, "-I", f], check=True)          # env flatgfa_file_inplace
+        assert subprocess.run([fgfa, "-m", "-i", flat], capture_output=True, check=True).stdout == want, f

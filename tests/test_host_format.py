@@ -446,3 +446,41 @@ def test_random_gfa_round_trips_through_both_writers():
     with pytest.raises(pb.DepthError):                     # the limit itself
         pb.FlatGFA.parse_bytes(b"S\t1\tA\nL\t1\t+\t1\t+\t256M\n")
     assert pb.FlatGFA.parse_bytes(b"S\t1\tA\nL\t1\t+\t1\t+\t255M\n").format_gfa().endswith(b"255M\n")
+
+
+def test_preallocated_translation_like_the_reference_harness(golden, fgfa_bin, tmp_path):
+    """tests/turnt.toml `flatgfa_file_inplace`: `fgfa -m -p 128 -o x.inplace.flatgfa -I x.gfa ; fgfa -m -i
+    x.inplace.flatgfa` must print the input text.  The file's pools carry the capacities of
+    `Toc::estimate` (file.rs:136-158, from parse.rs:176-216's scan); with stdin input those of
+    `Toc::guess(p)` (file.rs:117-132); a pool that does not fit fails like the reference's fixed store."""
+    flat = str(tmp_path / "x.inplace.flatgfa")
+    for c in golden:
+        src = os.path.join(c["dir"], c["gfa"])
+        text = open(src, "rb").read()
+        if not text.endswith(b"\n"):
+            continue
+        subprocess.run([fgfa_bin, "-m", "-p", "128", "-o", flat, "-I", src], check=True)
+        assert subprocess.run([fgfa_bin, "-m", "-i", flat], capture_output=True, check=True).stdout == text, c["name"]
+        toc = np.fromfile(flat, dtype="<u8", count=23)
+        sizes = toc[1:].reshape(11, 2)
+        lines = text.split(b"\n")[:-1]
+        segs = sum(l.startswith(b"S") for l in lines)
+        links = sum(l.startswith(b"L") for l in lines)
+        paths = sum(l.startswith(b"P") for l in lines)
+        nbytes = lambda k: sum(len(l) for l in lines if l.startswith(k))
+        want_caps = [nbytes(b"H"), segs, paths, links, nbytes(b"P") // 3, nbytes(b"S"), (links + paths) * 2,
+                     links * 2 + paths * 4, paths * 512, links * 16, segs + links + paths + 8]
+        assert sizes[:, 1].tolist() == want_caps, c["name"]
+        assert (sizes[:, 0] <= sizes[:, 1]).all()
+        assert os.path.getsize(flat) == 184 + int((sizes[:, 1] * np.array([1, 24, 24, 16, 4, 1, 8, 4, 1, 1, 1], np.uint64)).sum())
+    # stdin: capacities are guessed from -p
+    text = open(os.path.join(GOLD, "ref_tiny.gfa"), "rb").read()
+    subprocess.run([fgfa_bin, "-m", "-p", "2", "-o", flat], input=text, check=True)
+    toc = np.fromfile(flat, dtype="<u8", count=23)
+    assert toc[1:].reshape(11, 2)[:, 1].tolist() == [128, 128, 2, 128, 4096, 2048, 512, 256, 128, 2048, 256]
+    assert subprocess.run([fgfa_bin, "-i", flat], capture_output=True, check=True).stdout == text
+    # too small a guess: the reference's fixed-size store panics, this build reports it
+    r = subprocess.run([fgfa_bin, "-m", "-p", "1", "-o", flat], input=text, capture_output=True)
+    assert r.returncode != 0 and b"capacity overflow" in r.stderr      # 2 paths do not fit 1 slot
+    r = subprocess.run([fgfa_bin, "-m", "-o", flat, "-I", os.path.join(GOLD, "ref_tiny.gfa"), "depth"], capture_output=True)
+    assert r.returncode != 0 or r.stdout                              # with a command -m is the ordinary flow
