@@ -321,6 +321,15 @@ class FlatGFA:
     def write_flatgfa(self, filename: str) -> None:            # lib.rs:129-133
         self._h.dump(filename)
 
+    def all_reads(self, gaf: str):                              # lib.rs:136-146
+        raise NotImplementedError("GAF parsing is outside the scope of this package (node-depth path only)")
+
+    def print_gaf_lookup(self, gaf: str) -> None:               # lib.rs:154-169
+        raise NotImplementedError("GAF lookup is outside the scope of this package (node-depth path only)")
+
+    def make_pangenotype_matrix(self, gaf_files):               # lib.rs:172-177
+        raise NotImplementedError("the pangenotype matrix is outside the scope of this package (node-depth path only)")
+
     # ---- depth operators (GPU) ----
     def depth(self):
         """(depth, uniq): per segment, how many path steps cross it and how many distinct paths do."""
