@@ -14,7 +14,7 @@ LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_de
 
 all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libflatgfa.a $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools build/depth_example
 
-$(OBJDIR)/depth_device.o: $(CSRC)/depth_device.cu $(CSRC)/depth_kernels.cuh include/fgfa_depth.h
+$(OBJDIR)/depth_device.o: $(CSRC)/depth_device.cu $(CSRC)/depth_kernels.cuh $(CSRC)/window_kernels.cuh include/fgfa_depth.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
@@ -56,7 +56,11 @@ build/depth_example: examples/depth.c include/flatgfa.h $(LIBDIR)/libflatgfa.so
 oracle:
 	$(MAKE) -C oracle
 
-tools: build/ubench build/sort_dedup_probe
+tools: build/ubench build/sort_dedup_probe build/ubench_win build/ubench_smem
+build/ubench_win: tools/ubench_win.cu $(CSRC)/window_kernels.cuh $(CSRC)/depth_kernels.cuh build/ubench
+	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench_win.cu build/depth_oracle.o build/synth.o -o $@
+build/ubench_smem: tools/ubench_smem.cu
+	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench_smem.cu -o $@
 build/sort_dedup_probe: tools/sort_dedup_probe.cu $(CSRC)/synth.cpp oracle/depth_oracle.c build/ubench
 	$(NVCC) $(ARCH) -O3 -std=c++17 tools/sort_dedup_probe.cu build/depth_oracle.o build/synth.o -o $@
 build/ubench: tools/ubench.cu tools/experimental_kernels.cuh $(CSRC)/depth_kernels.cuh $(CSRC)/synth.cpp oracle/depth_oracle.c

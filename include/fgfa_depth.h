@@ -84,6 +84,23 @@ int fgfa_depth_plan_feed(fgfa_depth_plan_t* plan, const uint32_t* d_steps, uint3
                          uint32_t path_hi, uint32_t* d_depth, uint32_t* d_uniq, void* cuda_stream);
 int fgfa_depth_plan_finish(fgfa_depth_plan_t* plan, uint32_t* d_uniq, void* cuda_stream);
 
+/* Engines.  A plan runs one of two implementations of the same loop nest (depth.rs:25-35):
+ *   FGFA_ENGINE_WINDOW  segment-major: a data-dependent pre-pass bins 256-step sub-chunks by
+ *                       segment window, then every window is counted in shared memory (depth
+ *                       counters + 32-path masks).  Default for pools of >= 64 Mi steps.
+ *   FGFA_ENGINE_STREAM  path-major: one L2 reduction per step, per-path seen-bitmap rows.  Default
+ *                       for small pools; always used with fgfa_depth_plan_use_bitmap().
+ * Both give the same (bit-exact) results; they differ in speed only.  set_engine synchronises the
+ * device and (re)allocates the seen scratch; FGFA_ERR_INVALID_ARG if the engine is not available
+ * for this plan (the window engine needs n_segs / 16384 * planes <= 12000 keys).  autotune samples
+ * the resident pool once (synchronises the stream): a pool whose consecutive steps jump further
+ * than a shared-memory window can hold gains nothing from windows and is given the stream engine.
+ * The environment variable FGFA_ENGINE=stream|window overrides both the default and autotune. */
+enum { FGFA_ENGINE_STREAM = 0, FGFA_ENGINE_WINDOW = 1 };
+int fgfa_depth_plan_set_engine(fgfa_depth_plan_t* plan, int engine);
+int fgfa_depth_plan_engine(const fgfa_depth_plan_t* plan);
+int fgfa_depth_plan_autotune(fgfa_depth_plan_t* plan, const uint32_t* d_steps, void* cuda_stream);
+
 /* Synchronise the stream and report the sticky device status of the runs since the
  * last call: FGFA_OK, FGFA_ERR_SEG_OOB or FGFA_ERR_CUDA. */
 int fgfa_depth_plan_status(fgfa_depth_plan_t* plan, void* cuda_stream);

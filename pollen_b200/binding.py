@@ -92,6 +92,9 @@ EXPORTS = {
     "fgfa_depth_plan_run_stream_only": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_exchange_uniq_depth": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "fgfa_depth_plan_set_uniq_width": (C.c_int, [C.c_void_p, C.c_int]),
+    "fgfa_depth_plan_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
+    "fgfa_depth_plan_engine": (C.c_int, [C.c_void_p]),
+    "fgfa_depth_plan_autotune": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_set_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_depth_plan_launches": (C.c_uint32, [C.c_void_p, C.c_int]),
     "fgfa_depth_plan_scratch_bytes": (C.c_size_t, [C.c_void_p]),
@@ -549,6 +552,21 @@ class DepthPlan:
 
     def launches(self, with_uniq: bool = True) -> int:
         return int(lib().fgfa_depth_plan_launches(self._h, 1 if with_uniq else 0))
+
+    ENGINES = ("stream", "window")
+
+    @property
+    def engine(self) -> str:
+        """"window" (segment-major shared-memory windows) or "stream" (path-major L2 reductions)."""
+        return self.ENGINES[int(lib().fgfa_depth_plan_engine(self._h))]
+
+    def set_engine(self, name: str) -> None:
+        _check(lib().fgfa_depth_plan_set_engine(self._h, self.ENGINES.index(name)))
+
+    def autotune(self, d_steps, stream: int = 0) -> str:
+        """Sample the resident pool once and keep the engine that suits it; returns its name."""
+        _check(lib().fgfa_depth_plan_autotune(self._h, self._ptr(d_steps), stream or None))
+        return self.engine
 
     @property
     def scratch_bytes(self) -> int:

@@ -1,9 +1,15 @@
 // Device plan + C ABI of the B200 node-depth engine (see include/fgfa_depth.h).
 //
 // Replaces the loop nest of the reference's seg_depth_with_uniq / seg_depth
-// (flatgfa/src/ops/depth.rs:15-56) with kernel A (step stream) + kernel B (seen-bitmap
-// population count) from depth_kernels.cuh.  No CPU compute path exists here: every
-// entry point fails with FGFA_ERR_NO_DEVICE when CUDA is unavailable.
+// (flatgfa/src/ops/depth.rs:15-56).  Two engines:
+//   window  (default for large pools) segment-major: pre-pass S1-S3 bins 256-step sub-chunks by
+//           segment window, kernel W counts every window in shared memory (depth counters +
+//           32-path masks), kernel B2 popcounts the mask planes          -- window_kernels.cuh
+//   stream  path-major: kernel A streams the pool with one L2 reduction per step and per-path
+//           seen-bitmap rows, kernel B popcounts the rows                 -- depth_kernels.cuh
+//           (small pools, locality-free pools, and the multi-GPU exchange kernel X)
+// No CPU compute path exists here: every entry point fails with FGFA_ERR_NO_DEVICE when CUDA
+// is unavailable.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -17,6 +23,7 @@
 
 #include "../../include/fgfa_depth.h"
 #include "depth_kernels.cuh"
+#include "window_kernels.cuh"
 
 namespace {
 
@@ -46,6 +53,11 @@ constexpr size_t kDefaultBitmapBudget = 64ull << 20;  // stays resident in the 1
 constexpr int kBlocksPerSM = 5;
 constexpr int kGridPerSM = 10;
 constexpr int kPopMinBlocks = 4;       // kernel B register cap (measured, see profiles/)
+// kernel W: 8 rows of 32 steps per sub-chunk, 2 sub-chunks of loads in flight per warp (measured, profiles/r2_*)
+constexpr int kWinRows = 8, kWinStages = 2;
+// the window engine pays a pre-pass (3 launches) and a per-CTA window set-up: below this many
+// steps the stream engine is faster (config B, 20 M steps: 0.05 ms against 0.09 ms)
+constexpr uint64_t kWindowMinSteps = 64ull << 20;
 
 }  // namespace
 
@@ -70,6 +82,21 @@ struct fgfa_depth_plan {
     bool uniq_started = false;
     bool bitmap_dirty = false;             // seen-bits recorded that no kernel B has consumed yet
     int feed_mode = -1;                    // -1: no feed yet; 0: depth only; 1: depth + uniq (fixed per begin..finish)
+    // ---- window engine (window_kernels.cuh) ----
+    int engine = 0;                        // 0 = stream (kernels A/B), 1 = window (S1-S3, W, B2)
+    bool win_eligible = false;
+    size_t budget = 0;                     // seen-scratch budget the plan was created with
+    uint32_t sub_shift = 8;                // 256-step sub-chunks
+    std::vector<uint32_t> h_sub_prefix;    // sub-chunks before path p, [n_paths+1]
+    uint32_t *d_sub_prefix = nullptr, *d_span_s = nullptr, *d_span_e = nullptr;
+    uint32_t *d_keyrank = nullptr, *d_hist = nullptr, *d_key_total = nullptr, *d_key_begin = nullptr, *d_ticket = nullptr;
+    uint2* d_entries = nullptr;
+    uint32_t* d_masks = nullptr;           // [planes_per_pass][plane_pitch] path-mask planes, zero between runs
+    uint64_t plane_pitch = 0;
+    uint32_t planes_per_pass = 0;
+    uint32_t max_blocks = 0;
+    uint32_t bitmap_rows = 1;              // rows the stream engine's bitmap may hold (from the budget)
+    uint32_t bitmap_alloc_rows = 0;        // rows currently allocated in d_bitmap (own_bitmap only)
 };
 
 namespace {
@@ -101,6 +128,102 @@ int build_tables(fgfa_depth_plan* pl, uint32_t misalign) {
     if (chunks)
         CU(cudaMemcpy(pl->d_chunks, table.data(), (size_t)chunks * sizeof(fgfa::ChunkDesc), cudaMemcpyHostToDevice));
     pl->misalign = misalign;
+    // ---- window engine tables: sub-chunk prefix + shifted spans ----
+    pl->h_sub_prefix.assign((size_t)n + 1, 0u);
+    const uint32_t sub = 1u << pl->sub_shift;
+    uint64_t subs = 0;
+    std::vector<uint32_t> ss(n), se(n);
+    for (uint32_t p = 0; p < n; ++p) {
+        const uint64_t sp = (uint64_t)pl->h_start[p] + misalign, ep = (uint64_t)pl->h_end[p] + misalign;
+        ss[p] = (uint32_t)sp;
+        se[p] = (uint32_t)ep;
+        if (ep > sp) subs += (ep - (sp & ~31ull) + sub - 1) / sub;
+        pl->h_sub_prefix[p + 1] = (uint32_t)std::min<uint64_t>(subs, 0xFFFFFFFFull);
+    }
+    if (pl->win_eligible && subs < 0xFFFFFFFFull && n) {
+        CU(cudaMemcpy(pl->d_sub_prefix, pl->h_sub_prefix.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(pl->d_span_s, ss.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(pl->d_span_e, se.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    return FGFA_OK;
+}
+
+// Window engine over paths [lo, hi), which must lie inside one pass (a pass = the paths whose
+// mask planes fit the scratch).  pre-pass S1-S3 + kernel W.
+int launch_window(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t lo, uint32_t hi,
+                  uint32_t* d_depth, bool with_seen, cudaStream_t st) {
+    const uint32_t n_sub = pl->h_sub_prefix[hi] - pl->h_sub_prefix[lo];
+    if (n_sub == 0) return FGFA_OK;
+    const uint32_t pass_start = (lo / pl->rows_per_batch) * pl->rows_per_batch;
+    const uint32_t batch_lo = with_seen ? (lo - pass_start) >> 5 : 0u;
+    const uint32_t batch_hi = with_seen ? (hi - 1 - pass_start) >> 5 : 0u;
+    fgfa::BinParams B{};
+    B.steps = d_steps_aligned;
+    B.sub_prefix = pl->d_sub_prefix;
+    B.span_s = pl->d_span_s;
+    B.span_e = pl->d_span_e;
+    B.path_lo = lo;
+    B.path_hi = hi;
+    B.mask_path_lo = pass_start + 32u * batch_lo;
+    B.sub_shift = pl->sub_shift;
+    B.n_segs = pl->n_segs;
+    B.bin_segs = fgfa::win_bin(with_seen);
+    B.n_bins = (pl->n_segs + B.bin_segs - 1) / B.bin_segs;
+    B.n_batches = batch_hi - batch_lo + 1;
+    B.n_keys = B.n_bins * B.n_batches;
+    B.n_blocks = (n_sub + fgfa::kBinBlock - 1) / fgfa::kBinBlock;
+    B.max_span = 2 * fgfa::kWinHalo;
+    B.keyrank = pl->d_keyrank;
+    B.hist = pl->d_hist;
+    B.key_total = pl->d_key_total;
+    B.key_begin = pl->d_key_begin;
+    B.ticket = pl->d_ticket;
+    B.entries = pl->d_entries;
+    fgfa::k_bin_rank<<<B.n_blocks, fgfa::kBinThreads, (size_t)(B.n_keys + 1) * 4, st>>>(B);
+    fgfa::k_bin_rowscan<<<B.n_keys + 1, fgfa::kScanThreads, 0, st>>>(B);
+    fgfa::k_bin_scatter<<<B.n_blocks, fgfa::kBinThreads, 0, st>>>(B);
+    CU(cudaGetLastError());
+    fgfa::WindowParams W{};
+    W.steps = d_steps_aligned;
+    W.entries = pl->d_entries;
+    W.key_begin = pl->d_key_begin;
+    W.span_s = pl->d_span_s;
+    W.span_e = pl->d_span_e;
+    W.n_keys = B.n_keys;
+    W.n_batches = B.n_batches;
+    W.path_lo = B.mask_path_lo;
+    W.n_segs = pl->n_segs;
+    W.plane_pitch = pl->plane_pitch;
+    W.unit = 1;
+    W.depth = d_depth;
+    W.masks = with_seen ? pl->d_masks + (size_t)batch_lo * pl->plane_pitch : nullptr;
+    W.err = pl->d_err;
+    W.stats = nullptr;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)pl->sms, std::max(1u, (n_sub + 31) / 32));
+    if (pl->probe_before) CU(cudaEventRecord(pl->probe_before, st));
+    if (with_seen)
+        fgfa::k_window_count<kWinRows, kWinStages, true><<<grid, fgfa::kWinThreads, fgfa::window_smem_bytes(true), st>>>(W);
+    else
+        fgfa::k_window_count<kWinRows, kWinStages, false><<<grid, fgfa::kWinThreads, fgfa::window_smem_bytes(false), st>>>(W);
+    CU(cudaGetLastError());
+    if (pl->probe_after) CU(cudaEventRecord(pl->probe_after, st));
+    pl->probe_before = pl->probe_after = nullptr;
+    return FGFA_OK;
+}
+
+// kernel B2 over the first `planes` mask planes.
+int launch_mask_count(fgfa_depth_plan* pl, uint32_t planes, void* d_uniq, bool accumulate, cudaStream_t st) {
+    if (pl->n_segs == 0) return FGFA_OK;
+    fgfa::MaskCountParams Q{};
+    Q.masks = pl->d_masks;
+    Q.n_planes = planes;
+    Q.plane_pitch = pl->plane_pitch;
+    Q.n_segs = pl->n_segs;
+    Q.uniq = d_uniq;
+    Q.accumulate = accumulate ? 1 : 0;
+    Q.uniq_bytes = pl->uniq_bytes;
+    fgfa::k_uniq_from_masks<<<(pl->n_segs + 1023) / 1024, 256, 0, st>>>(Q);
+    CU(cudaGetLastError());
     return FGFA_OK;
 }
 
@@ -156,6 +279,35 @@ int launch_popcount(fgfa_depth_plan* pl, uint32_t rows, uint32_t* d_uniq, bool a
     const uint32_t grid = (pl->n_words + fgfa::kPopThreads - 1) / fgfa::kPopThreads;
     fgfa::k_uniq_popcount<kPopMinBlocks><<<grid, fgfa::kPopThreads, 0, st>>>(Q);
     CU(cudaGetLastError());
+    return FGFA_OK;
+}
+
+// Make `engine` the plan's engine and make sure its seen scratch exists (zeroed).
+int select_engine(fgfa_depth_plan* pl, int engine) {
+    if (engine == 1) {
+        if (!pl->win_eligible) return fail(FGFA_ERR_INVALID_ARG, "the window engine is not available for this plan");
+        const size_t bytes = (size_t)pl->plane_pitch * 4 * pl->planes_per_pass;
+        if (!pl->d_masks) {
+            CU(cudaMalloc(&pl->d_masks, std::max<size_t>(bytes, 4)));
+            CU(cudaMemset(pl->d_masks, 0, std::max<size_t>(bytes, 4)));
+            pl->scratch_bytes += bytes;
+        }
+        pl->rows_per_batch = (uint32_t)std::min<uint64_t>(32ull * pl->planes_per_pass, 0x7FFFFFE0u);
+    } else if (engine == 0) {
+        if (pl->own_bitmap && pl->bitmap_alloc_rows < pl->bitmap_rows) {
+            cudaFree(pl->d_bitmap);
+            pl->d_bitmap = nullptr;
+            const size_t bytes = std::max<size_t>((size_t)pl->words_per_row * 4 * pl->bitmap_rows, 4);
+            CU(cudaMalloc(&pl->d_bitmap, bytes));
+            CU(cudaMemset(pl->d_bitmap, 0, bytes));
+            pl->bitmap_alloc_rows = pl->bitmap_rows;
+            pl->scratch_bytes += bytes;
+        }
+        if (pl->own_bitmap) pl->rows_per_batch = pl->bitmap_rows;
+    } else {
+        return fail(FGFA_ERR_INVALID_ARG, "engine must be 0 (stream) or 1 (window)");
+    }
+    pl->engine = engine;
     return FGFA_OK;
 }
 
@@ -236,13 +388,55 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
             if (std::atoll(env) > 0) budget = (size_t)std::atoll(env) << 20;
     uint64_t rows = row_bytes ? std::max<uint64_t>(1, budget / row_bytes) : 1;
     rows = std::min<uint64_t>(rows, std::max<uint32_t>(1u, n_paths));
-    pl->rows_per_batch = (uint32_t)rows;
-    const size_t bitmap_bytes = std::max<size_t>(row_bytes * rows, 4);
+    pl->rows_per_batch = (uint32_t)rows;   // (select_engine() below has the last word)
+    pl->budget = budget;
+    pl->bitmap_rows = (uint32_t)rows;
 #define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(cuda_fail(e_, #x)); } while (0)
-    CUB_(cudaMalloc(&pl->d_bitmap, bitmap_bytes));
     CUB_(cudaMalloc(&pl->d_err, 4));
-    CUB_(cudaMemset(pl->d_bitmap, 0, bitmap_bytes));
     CUB_(cudaMemset(pl->d_err, 0, 4));
+    // ---- window engine: eligible when every launch's key table fits S1's shared memory ----
+    int engine = 0;
+    {
+        const uint32_t bins = (n_segs + fgfa::win_bin(true) - 1) / fgfa::win_bin(true);
+        uint64_t subs = 0;
+        const uint32_t sub = 1u << pl->sub_shift;
+        for (uint32_t p = 0; p < n_paths; ++p)
+            if (h_span_end[p] > h_span_start[p]) subs += ((uint64_t)h_span_end[p] + 3 - (h_span_start[p] & ~31u) + sub - 1) / sub;
+        pl->plane_pitch = ((uint64_t)n_segs + 31) & ~31ull;
+        const uint64_t plane_bytes = pl->plane_pitch * 4;
+        uint64_t planes = plane_bytes ? std::max<uint64_t>(1, budget / plane_bytes) : 1;
+        planes = std::min<uint64_t>(planes, ((uint64_t)std::max(n_paths, 1u) + 31) / 32);
+        if (bins) planes = std::min<uint64_t>(planes, (fgfa::kMaxKeys - 2) / bins);
+        pl->win_eligible = n_paths > 0 && n_paths < 0x7FFFFFFFu && n_segs > 0 && bins + 2 <= fgfa::kMaxKeys && planes >= 1 &&
+                           subs + n_paths < 0xFFFFFFF0ull;
+        engine = pl->win_eligible && n_steps >= kWindowMinSteps ? 1 : 0;
+        if (const char* env = std::getenv("FGFA_ENGINE")) {
+            if (!std::strcmp(env, "stream")) engine = 0;
+            else if (!std::strcmp(env, "window") && pl->win_eligible) engine = 1;
+        }
+        if (pl->win_eligible) {
+            pl->planes_per_pass = (uint32_t)planes;
+            pl->max_blocks = (uint32_t)((subs + n_paths + fgfa::kBinBlock - 1) / fgfa::kBinBlock + 1);
+            const uint64_t keys = (uint64_t)bins * planes + 2;
+            CUB_(cudaMalloc(&pl->d_sub_prefix, ((size_t)n_paths + 1) * 4));
+            CUB_(cudaMalloc(&pl->d_span_s, (size_t)n_paths * 4));
+            CUB_(cudaMalloc(&pl->d_span_e, (size_t)n_paths * 4));
+            CUB_(cudaMalloc(&pl->d_keyrank, (size_t)(subs + n_paths + 1) * 4));
+            CUB_(cudaMalloc(&pl->d_entries, (size_t)(subs + n_paths + 1) * 8));
+            CUB_(cudaMalloc(&pl->d_hist, (size_t)keys * pl->max_blocks * 4));
+            CUB_(cudaMalloc(&pl->d_key_total, (size_t)keys * 4));
+            CUB_(cudaMalloc(&pl->d_key_begin, (size_t)(keys + 1) * 4));
+            CUB_(cudaMalloc(&pl->d_ticket, 8));
+            CUB_(cudaMemset(pl->d_ticket, 0, 8));
+            pl->scratch_bytes += (size_t)(subs + n_paths + 1) * 12 + (size_t)keys * pl->max_blocks * 4;
+            cudaFuncSetAttribute(fgfa::k_window_count<kWinRows, kWinStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::window_smem_bytes(true));
+            cudaFuncSetAttribute(fgfa::k_window_count<kWinRows, kWinStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::window_smem_bytes(false));
+        }
+    }
+    {
+        int rc = select_engine(pl, engine);
+        if (rc) return bail(rc);
+    }
 #undef CUB_
     // kernel A wants 6 CTAs x 32 KiB of shared memory per SM: ask for the large carve-out
     cudaFuncSetAttribute(fgfa::k_step_stream_merged<kBlocksPerSM, fgfa::kSeenWindow>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -267,7 +461,7 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
     }
     int rc = build_tables(pl, 0);
     if (rc) return bail(rc);
-    pl->scratch_bytes = bitmap_bytes + pl->chunk_capacity * sizeof(fgfa::ChunkDesc) + 4;
+    pl->scratch_bytes += pl->chunk_capacity * sizeof(fgfa::ChunkDesc) + 4;
     *out = pl;
     return FGFA_OK;
 }
@@ -277,6 +471,10 @@ void fgfa_depth_plan_destroy(fgfa_depth_plan_t* pl) {
     cudaFree(pl->d_chunks);
     if (pl->own_bitmap) cudaFree(pl->d_bitmap);
     cudaFree(pl->d_err);
+    cudaFree(pl->d_sub_prefix); cudaFree(pl->d_span_s); cudaFree(pl->d_span_e);
+    cudaFree(pl->d_keyrank); cudaFree(pl->d_entries); cudaFree(pl->d_hist);
+    cudaFree(pl->d_key_total); cudaFree(pl->d_key_begin); cudaFree(pl->d_ticket);
+    cudaFree(pl->d_masks);
     delete pl;
 }
 
@@ -284,7 +482,10 @@ int fgfa_depth_plan_begin(fgfa_depth_plan_t* pl, uint32_t* d_depth, void* cuda_s
     if (!pl || (!d_depth && pl->n_segs)) return fail(FGFA_ERR_INVALID_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (pl->n_segs) CU(cudaMemsetAsync(d_depth, 0, (size_t)pl->n_segs * 4, st));  // depth.rs:17 vec![0; n]
-    if (pl->bitmap_dirty && pl->own_bitmap) {   // an earlier begin..finish run was abandoned half way
+    if (pl->bitmap_dirty && pl->engine == 1) {  // an earlier begin..finish run was abandoned half way
+        CU(cudaMemsetAsync(pl->d_masks, 0, (size_t)pl->plane_pitch * 4 * pl->planes_per_pass, st));
+        pl->bitmap_dirty = false;
+    } else if (pl->bitmap_dirty && pl->own_bitmap) {
         CU(cudaMemsetAsync(pl->d_bitmap, 0, (size_t)pl->words_per_row * 4 * pl->rows_per_batch, st));
         pl->bitmap_dirty = false;
     }
@@ -314,12 +515,14 @@ int fgfa_depth_plan_feed(fgfa_depth_plan_t* pl, const uint32_t* d_steps, uint32_
     while (lo < path_hi) {
         const uint32_t batch_end = std::min<uint64_t>(pl->n_paths, ((uint64_t)lo / pl->rows_per_batch + 1) * pl->rows_per_batch);
         const uint32_t hi = std::min(path_hi, batch_end);
-        int rc = launch_stream(pl, base, lo, hi, d_depth, with_seen, st);
+        int rc = pl->engine == 1 ? launch_window(pl, base, lo, hi, d_depth, with_seen, st)
+                                 : launch_stream(pl, base, lo, hi, d_depth, with_seen, st);
         if (rc) return rc;
         if (with_seen) pl->bitmap_dirty = true;
-        if (with_seen && hi == batch_end) {  // this bitmap batch is complete: fold it into uniq
+        if (with_seen && hi == batch_end) {  // this batch of seen rows / mask planes is complete: fold it into uniq
             const uint32_t batch_start = (lo / pl->rows_per_batch) * pl->rows_per_batch;
-            rc = launch_popcount(pl, batch_end - batch_start, d_uniq, pl->uniq_started, st);
+            rc = pl->engine == 1 ? launch_mask_count(pl, (batch_end - batch_start + 31) / 32, d_uniq, pl->uniq_started, st)
+                                 : launch_popcount(pl, batch_end - batch_start, d_uniq, pl->uniq_started, st);
             if (rc) return rc;
             pl->uniq_started = true;
             pl->bitmap_dirty = false;
@@ -371,6 +574,7 @@ int fgfa_depth_plan_use_bitmap(fgfa_depth_plan_t* pl, void* d_bitmap, size_t byt
     if (pl->own_bitmap) cudaFree(pl->d_bitmap);
     pl->d_bitmap = static_cast<uint32_t*>(d_bitmap);
     pl->own_bitmap = false;
+    pl->engine = 0;                                             // seen-bitmap rows are the stream engine's
     pl->rows_per_batch = std::max<uint32_t>(pl->n_paths, 1u);   // one batch: every path has its row
     return FGFA_OK;
 }
@@ -378,7 +582,8 @@ int fgfa_depth_plan_use_bitmap(fgfa_depth_plan_t* pl, void* d_bitmap, size_t byt
 int fgfa_depth_plan_run_stream_only(fgfa_depth_plan_t* pl, const uint32_t* d_steps, uint32_t* d_depth,
                                     void* cuda_stream) {
     if (!pl || (!d_depth && pl->n_segs)) return fail(FGFA_ERR_INVALID_ARG, "null argument");
-    if (pl->rows_per_batch < pl->n_paths) return fail(FGFA_ERR_INVALID_ARG, "the bitmap must hold every path (one batch)");
+    if (pl->engine != 0 || pl->rows_per_batch < pl->n_paths)
+        return fail(FGFA_ERR_INVALID_ARG, "needs the stream engine with a bitmap that holds every path (fgfa_depth_plan_use_bitmap)");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (pl->n_segs) CU(cudaMemsetAsync(d_depth, 0, (size_t)pl->n_segs * 4, st));
     if (pl->n_paths == 0 || pl->n_steps == 0) return FGFA_OK;
@@ -440,6 +645,55 @@ int fgfa_exchange_uniq_depth(int n_ranks, int rank, const void* const* bitmaps, 
     return FGFA_OK;
 }
 
+int fgfa_depth_plan_set_engine(fgfa_depth_plan_t* pl, int engine) {
+    if (!pl) return fail(FGFA_ERR_INVALID_ARG, "null plan");
+    if (!pl->own_bitmap && engine != 0) return fail(FGFA_ERR_INVALID_ARG, "a plan with an external bitmap runs the stream engine");
+    if (pl->next_path != 0 && pl->next_path != pl->n_paths) return fail(FGFA_ERR_INVALID_ARG, "a begin..finish run is in progress");
+    CU(cudaDeviceSynchronize());
+    return select_engine(pl, engine);
+}
+
+int fgfa_depth_plan_engine(const fgfa_depth_plan_t* pl) { return pl ? pl->engine : -1; }
+
+int fgfa_depth_plan_autotune(fgfa_depth_plan_t* pl, const uint32_t* d_steps, void* cuda_stream) {
+    if (!pl) return fail(FGFA_ERR_INVALID_ARG, "null plan");
+    if (!pl->win_eligible || !pl->own_bitmap || pl->n_steps == 0) return FGFA_OK;
+    if (!d_steps) return fail(FGFA_ERR_INVALID_ARG, "d_steps is null");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint32_t* base = d_steps;
+    int rc = prepare_pointer(pl, d_steps, &base);
+    if (rc) return rc;
+    const uint32_t n_sub = pl->h_sub_prefix[pl->n_paths];
+    if (n_sub == 0) return FGFA_OK;
+    const uint32_t samples = std::min<uint32_t>(n_sub, 16384u);
+    fgfa::BinParams B{};
+    B.steps = base;
+    B.sub_prefix = pl->d_sub_prefix;
+    B.span_s = pl->d_span_s;
+    B.span_e = pl->d_span_e;
+    B.path_lo = 0;
+    B.path_hi = pl->n_paths;
+    B.sub_shift = pl->sub_shift;
+    B.n_segs = pl->n_segs;
+    B.max_span = 2 * fgfa::kWinHalo;
+    B.ticket = pl->d_ticket;
+    CU(cudaMemsetAsync(pl->d_ticket, 0, 8, st));
+    fgfa::k_sample_spans<<<(samples + 255) / 256, 256, 0, st>>>(B, samples, n_sub / samples);
+    CU(cudaGetLastError());
+    uint32_t h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, pl->d_ticket, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(pl->d_ticket, 0, 8, st));
+    CU(cudaStreamSynchronize(st));
+    // h[1] of h[0] sampled sub-chunks jump further than a window can hold: such pools gain nothing
+    // from shared-memory windows (config U), and the stream engine handles them better.
+    const bool scattered = h[0] > 0 && 2ull * h[1] > h[0];
+    const int want = (!scattered && pl->n_steps >= kWindowMinSteps) ? 1 : 0;
+    const char* env = std::getenv("FGFA_ENGINE");
+    if (env && (!std::strcmp(env, "stream") || !std::strcmp(env, "window"))) return FGFA_OK;   // forced
+    if (want == pl->engine) return FGFA_OK;
+    return fgfa_depth_plan_set_engine(pl, want);
+}
+
 int fgfa_depth_plan_set_uniq_width(fgfa_depth_plan_t* pl, int bytes) {
     if (!pl || (bytes != 1 && bytes != 4)) return fail(FGFA_ERR_INVALID_ARG, "uniq width must be 1 or 4 bytes");
     if (bytes == 1 && pl->n_paths > 255) return fail(FGFA_ERR_INVALID_ARG, "u8 uniq counters need <= 255 paths");
@@ -487,6 +741,7 @@ int fgfa_depth_plan_path_sums(fgfa_depth_plan_t* pl, const uint32_t* d_steps, co
 uint32_t fgfa_depth_plan_launches(const fgfa_depth_plan_t* pl, int with_uniq) {
     if (!pl || pl->n_paths == 0) return 0;
     const uint32_t batches = (pl->n_paths + pl->rows_per_batch - 1) / pl->rows_per_batch;
+    if (pl->engine == 1) return with_uniq ? 5 * batches : 4 * batches;   // S1, S2, S3, W (+ B2)
     return with_uniq ? 2 * batches : batches;
 }
 

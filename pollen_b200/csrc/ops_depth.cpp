@@ -35,6 +35,8 @@ struct Workspace {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     fgfa_depth_plan_t* plan = nullptr;
     uint64_t plan_key[4] = {0, 0, 0, 0};
+    std::vector<uint32_t> plan_start, plan_end;   // the cached plan's span table (exact comparison)
+    std::string plan_env;                         // FGFA_ENGINE / FGFA_SEEN_MODE the plan was created under
 
     void release() {
         if (plan) fgfa_depth_plan_destroy(plan);
@@ -64,9 +66,47 @@ int cuda_rc(cudaError_t e) {
 
 constexpr uint64_t kUploadGroupSteps = 16ull << 20;   // 64 MiB of Handle words per upload
 
-uint64_t fnv1a(const uint32_t* a, size_t n, uint64_t h) {
-    for (size_t i = 0; i < n; ++i) { h ^= a[i]; h *= 0x100000001B3ull; }
-    return h;
+// The workspace's plan for this graph shape: re-used when counts, span tables (compared exactly,
+// not by hash) and the engine-selecting environment are unchanged, rebuilt otherwise.
+int cached_plan(Workspace& W, const uint32_t* h_span_start, const uint32_t* h_span_end, uint32_t n_paths,
+                uint32_t n_segs, uint64_t n_steps) {
+    const uint64_t key[4] = {n_paths, n_segs, n_steps, 0};
+    std::string env;
+    for (const char* name : {"FGFA_ENGINE", "FGFA_SEEN_MODE", "FGFA_BITMAP_BUDGET_MB"}) {
+        const char* v = std::getenv(name);
+        env += v ? v : "";
+        env += '|';
+    }
+    const bool same = W.plan && std::memcmp(key, W.plan_key, sizeof key) == 0 && env == W.plan_env &&
+                      W.plan_start.size() == n_paths &&
+                      (n_paths == 0 || (std::memcmp(W.plan_start.data(), h_span_start, (size_t)n_paths * 4) == 0 &&
+                                        std::memcmp(W.plan_end.data(), h_span_end, (size_t)n_paths * 4) == 0));
+    if (same) return FGFA_OK;
+    if (W.plan) fgfa_depth_plan_destroy(W.plan);
+    W.plan = nullptr;
+    int rc = fgfa_depth_plan_create(&W.plan, h_span_start, h_span_end, n_paths, n_segs, n_steps, 0);
+    if (rc) return rc;
+    std::memcpy(W.plan_key, key, sizeof key);
+    W.plan_start.assign(h_span_start, h_span_start + n_paths);
+    W.plan_end.assign(h_span_end, h_span_end + n_paths);
+    W.plan_env = env;
+    return FGFA_OK;
+}
+
+// Engine choice for host steps (the device-resident form is fgfa_depth_plan_autotune): a pool whose
+// sub-chunks jump further than a shared-memory window can hold (uniformly random ids) gains nothing
+// from the window engine.  4096 evenly spaced 256-step sub-chunks, first against last handle.
+bool host_pool_is_scattered(const uint32_t* h_steps, uint64_t n_steps) {
+    constexpr uint64_t kSub = 256, kSamples = 4096, kMaxSpan = 2 * 6144;
+    if (n_steps < 2 * kSub * kSamples) return false;
+    const uint64_t stride = n_steps / kSamples;
+    uint64_t far = 0;
+    for (uint64_t i = 0; i < kSamples; ++i) {
+        const uint64_t a = i * stride;
+        const uint32_t h0 = h_steps[a] >> 1, h1 = h_steps[a + kSub - 1] >> 1;
+        far += (h0 > h1 ? h0 - h1 : h1 - h0) > kMaxSpan;
+    }
+    return 2 * far > kSamples;
 }
 
 int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, size_t aux_bytes = 0) {
@@ -142,14 +182,12 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
     const bool want_uniq = uniq_out != nullptr;
     int rc = ensure_workspace(W, n_steps, n_segs);
     if (rc) return rc;
-    const uint64_t key[4] = {n_paths, n_segs, n_steps,
-                             fnv1a(h_span_end, n_paths, fnv1a(h_span_start, n_paths, 0xCBF29CE484222325ull))};
-    if (!W.plan || std::memcmp(key, W.plan_key, sizeof key) != 0) {
-        if (W.plan) fgfa_depth_plan_destroy(W.plan);
-        W.plan = nullptr;
-        rc = fgfa_depth_plan_create(&W.plan, h_span_start, h_span_end, n_paths, n_segs, n_steps, 0);
+    rc = cached_plan(W, h_span_start, h_span_end, n_paths, n_segs, n_steps);
+    if (rc) return rc;
+    if (!std::getenv("FGFA_ENGINE") && fgfa_depth_plan_engine(W.plan) == FGFA_ENGINE_WINDOW &&
+        host_pool_is_scattered(h_steps, n_steps)) {
+        rc = fgfa_depth_plan_set_engine(W.plan, FGFA_ENGINE_STREAM);
         if (rc) return rc;
-        std::memcpy(W.plan_key, key, sizeof key);
     }
     uint32_t* d_depth = W.out;
     uint32_t* d_uniq = want_uniq ? W.out + n_segs : nullptr;
@@ -219,15 +257,8 @@ int fgfa_path_depth_steps(const uint32_t* h_steps, uint64_t n_steps, const uint3
     const size_t scratch_bytes = std::max<size_t>((size_t)n_segs * 8, 16);
     int rc = ensure_workspace(W, n_steps, n_segs, scratch_bytes + sums_bytes);
     if (rc) return rc;
-    const uint64_t key[4] = {n_paths, n_segs, n_steps,
-                             fnv1a(h_span_end, n_paths, fnv1a(h_span_start, n_paths, 0xCBF29CE484222325ull))};
-    if (!W.plan || std::memcmp(key, W.plan_key, sizeof key) != 0) {
-        if (W.plan) fgfa_depth_plan_destroy(W.plan);
-        W.plan = nullptr;
-        rc = fgfa_depth_plan_create(&W.plan, h_span_start, h_span_end, n_paths, n_segs, n_steps, 0);
-        if (rc) return rc;
-        std::memcpy(W.plan_key, key, sizeof key);
-    }
+    rc = cached_plan(W, h_span_start, h_span_end, n_paths, n_segs, n_steps);
+    if (rc) return rc;
     uint32_t* d_depth = W.out;
     uint32_t* d_len = W.out + n_segs;
     uint64_t* d_sums = reinterpret_cast<uint64_t*>(static_cast<char*>(W.aux) + scratch_bytes);
@@ -339,15 +370,8 @@ int interval_depth_host(const uint32_t* h_steps, uint64_t n_steps, const uint32_
     const size_t scr1 = fgfa_interval_scratch_bytes(n, 0);
     int rc = ensure_workspace(W, n_steps, n_segs, off_bytes + scr1);
     if (rc) return rc;
-    const uint64_t key[4] = {n_paths, n_segs, n_steps,
-                             fnv1a(h_span_end, n_paths, fnv1a(h_span_start, n_paths, 0xCBF29CE484222325ull))};
-    if (!W.plan || std::memcmp(key, W.plan_key, sizeof key) != 0) {
-        if (W.plan) fgfa_depth_plan_destroy(W.plan);
-        W.plan = nullptr;
-        rc = fgfa_depth_plan_create(&W.plan, h_span_start, h_span_end, n_paths, n_segs, n_steps, 0);
-        if (rc) return rc;
-        std::memcpy(W.plan_key, key, sizeof key);
-    }
+    rc = cached_plan(W, h_span_start, h_span_end, n_paths, n_segs, n_steps);
+    if (rc) return rc;
     uint32_t* d_depth = W.out;
     uint32_t* d_len = W.out + n_segs;
     uint64_t* d_seg_end = static_cast<uint64_t*>(W.aux);
