@@ -90,7 +90,7 @@ struct fgfa_depth_plan {
     std::vector<uint32_t> h_sub_prefix;    // sub-chunks before path p, [n_paths+1]
     uint32_t *d_sub_prefix = nullptr, *d_span_s = nullptr, *d_span_e = nullptr;
     uint32_t *d_keyrank = nullptr, *d_hist = nullptr, *d_key_total = nullptr, *d_key_begin = nullptr, *d_ticket = nullptr;
-    uint2* d_entries = nullptr;
+    uint2 *d_entries = nullptr, *d_entry_tmp = nullptr;
     uint32_t* d_masks = nullptr;           // [planes_per_pass][plane_pitch] path-mask planes, zero between runs
     uint64_t plane_pitch = 0;
     uint32_t planes_per_pass = 0;
@@ -179,6 +179,7 @@ int launch_window(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     B.key_begin = pl->d_key_begin;
     B.ticket = pl->d_ticket;
     B.entries = pl->d_entries;
+    B.entry_tmp = pl->d_entry_tmp;
     fgfa::k_bin_rank<<<B.n_blocks, fgfa::kBinThreads, (size_t)(B.n_keys + 1) * 4, st>>>(B);
     fgfa::k_bin_rowscan<<<B.n_keys + 1, fgfa::kScanThreads, 0, st>>>(B);
     fgfa::k_bin_scatter<<<B.n_blocks, fgfa::kBinThreads, 0, st>>>(B);
@@ -423,14 +424,16 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
             CUB_(cudaMalloc(&pl->d_span_e, (size_t)n_paths * 4));
             CUB_(cudaMalloc(&pl->d_keyrank, (size_t)(subs + n_paths + 1) * 4));
             CUB_(cudaMalloc(&pl->d_entries, (size_t)(subs + n_paths + 1) * 8));
+            CUB_(cudaMalloc(&pl->d_entry_tmp, (size_t)(subs + n_paths + 1) * 8));
             CUB_(cudaMalloc(&pl->d_hist, (size_t)keys * pl->max_blocks * 4));
             CUB_(cudaMalloc(&pl->d_key_total, (size_t)keys * 4));
             CUB_(cudaMalloc(&pl->d_key_begin, (size_t)(keys + 1) * 4));
             CUB_(cudaMalloc(&pl->d_ticket, 8));
             CUB_(cudaMemset(pl->d_ticket, 0, 8));
-            pl->scratch_bytes += (size_t)(subs + n_paths + 1) * 12 + (size_t)keys * pl->max_blocks * 4;
+            pl->scratch_bytes += (size_t)(subs + n_paths + 1) * 20 + (size_t)keys * pl->max_blocks * 4;
             cudaFuncSetAttribute(fgfa::k_window_count<kWinRows, kWinStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::window_smem_bytes(true));
             cudaFuncSetAttribute(fgfa::k_window_count<kWinRows, kWinStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::window_smem_bytes(false));
+            cudaFuncSetAttribute(fgfa::k_bin_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fgfa::kMaxKeys * 4));
         }
     }
     {
@@ -472,7 +475,7 @@ void fgfa_depth_plan_destroy(fgfa_depth_plan_t* pl) {
     if (pl->own_bitmap) cudaFree(pl->d_bitmap);
     cudaFree(pl->d_err);
     cudaFree(pl->d_sub_prefix); cudaFree(pl->d_span_s); cudaFree(pl->d_span_e);
-    cudaFree(pl->d_keyrank); cudaFree(pl->d_entries); cudaFree(pl->d_hist);
+    cudaFree(pl->d_keyrank); cudaFree(pl->d_entries); cudaFree(pl->d_entry_tmp); cudaFree(pl->d_hist);
     cudaFree(pl->d_key_total); cudaFree(pl->d_key_begin); cudaFree(pl->d_ticket);
     cudaFree(pl->d_masks);
     delete pl;

@@ -78,6 +78,7 @@ struct BinParams {
     uint32_t* __restrict__ key_total;          // [n_keys + 1]
     uint32_t* __restrict__ key_begin;          // [n_keys + 2]
     uint32_t* __restrict__ ticket;             // zero between launches
+    uint2* __restrict__ entry_tmp;             // [n_sub] the entries in sub-chunk order (S1 -> S3)
     uint2* __restrict__ entries;               // [n_sub] {first element (128-byte aligned), path | edge}
 };
 
@@ -93,38 +94,59 @@ __device__ __forceinline__ uint32_t find_sub_path(const uint32_t* __restrict__ p
 // S1: key + rank inside the block + per-block histogram.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBinThreads) k_bin_rank(BinParams P) {
-    extern __shared__ uint32_t s_cnt[];            // [n_keys + 1]
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* const s_cnt = s_dyn;                 // [n_keys + 1]
+    __shared__ uint32_t s_h0[kBinBlock + 1];       // first handle (>> 1) of every sub-chunk of the block
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     for (uint32_t i = tid; i <= P.n_keys; i += kBinThreads) s_cnt[i] = 0u;
     const uint32_t d_lo = __ldg(P.sub_prefix + P.path_lo), d_hi = __ldg(P.sub_prefix + P.path_hi);
     const uint32_t sub = 1u << P.sub_shift;
-    uint32_t key[kBinRounds];
+    const uint32_t d0 = d_lo + blockIdx.x * kBinBlock;
+    // every sample is fetched ONCE (it costs a DRAM row activation): a sub-chunk's second sample is
+    // its successor's first handle, taken from shared memory
+    uint32_t path[kBinRounds], last_d[kBinRounds], span_e[kBinRounds];
 #pragma unroll
     for (uint32_t round = 0; round < kBinRounds; ++round) {
-        const uint32_t d = d_lo + blockIdx.x * kBinBlock + round * kBinThreads + tid;
-        key[round] = 0xFFFFFFFFu - lane;           // invalid lanes never match anybody
+        const uint32_t d = d0 + round * kBinThreads + tid;
+        path[round] = 0; last_d[round] = 0; span_e[round] = 0;
         if (d < d_hi) {
             const uint32_t p = find_sub_path(P.sub_prefix, P.path_lo, P.path_hi, d);
             const uint32_t s = __ldg(P.span_s + p), e = __ldg(P.span_e + p);
             const uint32_t a = (s & ~31u) + ((d - __ldg(P.sub_prefix + p)) << P.sub_shift);
-            const uint64_t nxt = (uint64_t)a + sub;
-            const uint32_t h0 = __ldg(P.steps + max(a, s)) >> 1;
-            const uint32_t h1 = __ldg(P.steps + (nxt < e ? (uint32_t)nxt : e - 1u)) >> 1;
-            const uint32_t span = h1 > h0 ? h1 - h0 : h0 - h1;
-            if (max(h0, h1) >= P.n_segs || span > P.max_span) key[round] = P.n_keys;
-            else key[round] = (uint32_t)(((uint64_t)h0 + h1) >> 1) / P.bin_segs * P.n_batches + (P.n_batches > 1 ? (p - P.mask_path_lo) >> 5 : 0u);
+            path[round] = p; span_e[round] = e;
+            last_d[round] = __ldg(P.sub_prefix + p + 1) - 1u;       // last sub-chunk of this path
+            s_h0[round * kBinThreads + tid] = __ldg(P.steps + max(a, s)) >> 1;
+            P.entry_tmp[d - d_lo] = make_uint2(a, p | ((a < s || (uint64_t)a + sub > e) ? kEdgeBit : 0u));
         }
+    }
+    if (tid == 0) {                                // the successor of the block's last sub-chunk
+        const uint32_t d = d0 + kBinBlock;
+        uint32_t v = 0;
+        if (d < d_hi) {
+            const uint32_t p = find_sub_path(P.sub_prefix, P.path_lo, P.path_hi, d);
+            const uint32_t s = __ldg(P.span_s + p);
+            v = __ldg(P.steps + max((s & ~31u) + ((d - __ldg(P.sub_prefix + p)) << P.sub_shift), s)) >> 1;
+        }
+        s_h0[kBinBlock] = v;
     }
     __syncthreads();
 #pragma unroll
     for (uint32_t round = 0; round < kBinRounds; ++round) {
-        const uint32_t d = d_lo + blockIdx.x * kBinBlock + round * kBinThreads + tid;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key[round]);
+        const uint32_t idx = round * kBinThreads + tid, d = d0 + idx;
+        uint32_t key = 0xFFFFFFFFu - lane;         // invalid lanes never match anybody
+        if (d < d_hi) {
+            const uint32_t h0 = s_h0[idx];
+            const uint32_t h1 = d < last_d[round] ? s_h0[idx + 1] : __ldg(P.steps + span_e[round] - 1u) >> 1;
+            const uint32_t span = h1 > h0 ? h1 - h0 : h0 - h1;
+            if (max(h0, h1) >= P.n_segs || span > P.max_span) key = P.n_keys;
+            else key = (uint32_t)(((uint64_t)h0 + h1) >> 1) / P.bin_segs * P.n_batches + (P.n_batches > 1 ? (path[round] - P.mask_path_lo) >> 5 : 0u);
+        }
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
         const uint32_t before = __popc(peers & ((1u << lane) - 1u));
         uint32_t base = 0;
-        if (d < d_hi && before == 0u) base = atomicAdd(&s_cnt[key[round]], __popc(peers));
+        if (d < d_hi && before == 0u) base = atomicAdd(&s_cnt[key], __popc(peers));
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(peers) - 1);
-        if (d < d_hi) P.keyrank[d - d_lo] = (key[round] << kRankBits) | (base + before);
+        if (d < d_hi) P.keyrank[d - d_lo] = (key << kRankBits) | (base + before);
     }
     __syncthreads();
     for (uint32_t i = tid; i <= P.n_keys; i += kBinThreads) P.hist[(size_t)i * P.n_blocks + blockIdx.x] = s_cnt[i];
@@ -225,19 +247,14 @@ __global__ void __launch_bounds__(kScanThreads) k_bin_rowscan(BinParams P) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(BinParams P) {
     const uint32_t d_lo = __ldg(P.sub_prefix + P.path_lo), d_hi = __ldg(P.sub_prefix + P.path_hi);
-    const uint32_t sub = 1u << P.sub_shift;
 #pragma unroll
     for (uint32_t round = 0; round < kBinRounds; ++round) {
         const uint32_t d = d_lo + blockIdx.x * kBinBlock + round * kBinThreads + threadIdx.x;
         if (d >= d_hi) continue;
         const uint32_t kr = P.keyrank[d - d_lo];
         const uint32_t key = kr >> kRankBits, rank = kr & ((1u << kRankBits) - 1u);
-        const uint32_t p = find_sub_path(P.sub_prefix, P.path_lo, P.path_hi, d);
-        const uint32_t s = __ldg(P.span_s + p), e = __ldg(P.span_e + p);
-        const uint32_t a = (s & ~31u) + ((d - __ldg(P.sub_prefix + p)) << P.sub_shift);
-        const bool edge = a < s || (uint64_t)a + sub > e;
         const uint32_t pos = P.key_begin[key] + P.hist[(size_t)key * P.n_blocks + blockIdx.x] + rank;
-        P.entries[pos] = make_uint2(a, p | (edge ? kEdgeBit : 0u));
+        P.entries[pos] = P.entry_tmp[d - d_lo];
     }
 }
 

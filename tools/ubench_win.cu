@@ -71,6 +71,12 @@ int main(int argc, char** argv) {
     unsigned long long* d_stats;
     CK(cudaMalloc(&d_stats, 16));
 
+    if (const char* g = getenv("UBENCH_L2_FETCH")) {
+        CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)));
+        size_t v = 0;
+        CK(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+        printf("cudaLimitMaxL2FetchGranularity = %zu\n", v);
+    }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     const int sms = prop.multiProcessorCount;
@@ -113,7 +119,7 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(d_prefix, prefix.data(), (cfg.n_paths + 1) * 4, cudaMemcpyHostToDevice));
         B.sub_prefix = d_prefix;
         uint32_t *d_keyrank, *d_hist, *d_key_begin, *d_key_total, *d_ticket, *d_masks;
-        uint2* d_entries;
+        uint2 *d_entries, *d_entry_tmp;
         const uint64_t pitch = ((uint64_t)cfg.n_segs + 31) & ~31ull;
         CK(cudaMalloc(&d_key_total, (size_t)(B.n_keys + 1) * 4));
         CK(cudaMalloc(&d_ticket, 4));
@@ -122,9 +128,10 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&d_hist, (size_t)(B.n_keys + 1) * std::max(B.n_blocks, 1u) * 4));
         CK(cudaMalloc(&d_key_begin, (size_t)(B.n_keys + 2) * 4));
         CK(cudaMalloc(&d_entries, (size_t)std::max(n_sub, 1u) * 8));
+        CK(cudaMalloc(&d_entry_tmp, (size_t)std::max(n_sub, 1u) * 8));
         CK(cudaMalloc(&d_masks, (size_t)B.n_batches * pitch * 4));
         CK(cudaMemset(d_masks, 0, (size_t)B.n_batches * pitch * 4));
-        B.keyrank = d_keyrank; B.hist = d_hist; B.key_begin = d_key_begin; B.entries = d_entries;
+        B.keyrank = d_keyrank; B.hist = d_hist; B.key_begin = d_key_begin; B.entries = d_entries; B.entry_tmp = d_entry_tmp;
         B.key_total = d_key_total; B.ticket = d_ticket;
         WindowParams W{};
         W.steps = d_steps; W.entries = d_entries; W.key_begin = d_key_begin; W.span_s = d_ss; W.span_e = d_se;
@@ -185,7 +192,7 @@ int main(int argc, char** argv) {
                    (bad_d | bad_u) ? "FAIL" : "PARITY OK");
         }
         cudaFree(d_key_total); cudaFree(d_ticket); cudaFree(d_prefix); cudaFree(d_keyrank); cudaFree(d_hist);
-        cudaFree(d_key_begin); cudaFree(d_entries); cudaFree(d_masks);
+        cudaFree(d_key_begin); cudaFree(d_entries); cudaFree(d_entry_tmp); cudaFree(d_masks);
     };
 
 #define SETUP(K, SM) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM)))
