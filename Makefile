@@ -10,7 +10,7 @@ CSRC      := pollen_b200/csrc
 LIBDIR    := pollen_b200/lib
 OBJDIR    := build/obj
 
-LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(OBJDIR)/ops_depth.o $(OBJDIR)/ops_window_depth.o $(OBJDIR)/flatbed.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/print.o $(OBJDIR)/capi.o
+LIB_OBJS  := $(OBJDIR)/depth_device.o $(OBJDIR)/tokenize.o $(OBJDIR)/interval_device.o $(OBJDIR)/depth_multi.o $(OBJDIR)/ops_depth.o $(OBJDIR)/ops_window_depth.o $(OBJDIR)/flatbed.o $(OBJDIR)/file.o $(OBJDIR)/parse.o $(OBJDIR)/print.o $(OBJDIR)/capi.o
 
 all: $(LIBDIR)/libflatgfa.so $(LIBDIR)/libflatgfa.a $(LIBDIR)/libfgfa_synth.so bin/fgfa oracle tools build/depth_example
 
@@ -32,10 +32,10 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.hpp) include/fgfa_depth.h incl
 
 $(LIBDIR)/libflatgfa.so: $(LIB_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS) -cudart static -lpthread
+	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS) -cudart static -lpthread -ldl
 
 # flatgfa-c/Cargo.toml:6-8 builds both a cdylib and a staticlib; link the archive with
-#   g++ app.o libflatgfa.a -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+#   g++ app.o libflatgfa.a -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread   (libnccl is dlopen'ed on first multi-GPU use)
 $(LIBDIR)/libflatgfa.a: $(LIB_OBJS)
 	@mkdir -p $(LIBDIR)
 	rm -f $@ && ar rcs $@ $(LIB_OBJS)

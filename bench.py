@@ -4,16 +4,21 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config C|B|E] [--impl ours|reference]
 
 One process per GPU (under torchrun for N > 1).  A "step" is one full pass of the hot
-path over the synthetic graph: zero the outputs, kernel A (step stream), kernel B
-(seen-bitmap popcount) and, for N > 1, the allreduce of [depth | uniq].  The workload is
+path over the synthetic graph: zero the outputs, the engine the plan chose -- window (pre-pass
+S1-S3, kernel W, kernel B2) or stream (kernel A, kernel B) -- and, for N > 1, the exchange of
+[depth | uniq].  The workload is
 BASELINE.json configs[2] (the 400M-step graph the metric is quoted on); at N > 1 the SAME
 graph is sharded by whole paths (configs[3]), so scaling is "strong".
 
 `value`     steps/s with the shard resident in HBM (CUDA events, max over ranks).
 `e2e`       the same metric through the host-buffer entry point: pinned host steps ->
             H2D -> kernels (-> allreduce) -> D2H of depth/uniq, every step.
-`roofline`  algorithmic bytes of kernel A / its CUDA-event duration inside the timed
-            region, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`roofline`  algorithmic bytes of the dominant kernel (W or A) / its CUDA-event duration inside
+            the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`parity`    after the timed region rank 0 recomputes the WHOLE graph with the oracle and compares
+            every depth and uniq value with what the GPUs hold; a mismatch exits non-zero.
+`extra_configs`  BASELINE.json configs[1] (B) and configs[4] (E) measured outside the main timed
+            region: B and E at N = 1, E again (one path per GPU) at N = 8.
 `cpu_baseline`  the oracle (C port of depth.rs:15-39, single thread like the reference); its
                 `path_parallel_variant` is a multi-threaded CPU figure that is NOT the reference's algorithm
             timed on this box, rank 0, N = 1 only.
@@ -151,15 +156,66 @@ def run_reference(args, cfg, rank):
     }))
 
 
-def workload_config(cfg, n_gpus, exchange=None):
+def workload_config(cfg, n_gpus):
+    """Identical for the product arm and the reference arm (the driver compares them)."""
     return {
-        **({"exchange": exchange} if exchange else {}),
         "workload": f"{cfg.name}: {cfg.description}",
         "n_segs": cfg.n_segs, "n_paths": cfg.n_paths, "n_steps": cfg.n_steps,
         "generator": "haplotype walk (SURVEY.md 8d), seed 0xB1011054" if cfg.kind == 0 else "see pollen_b200/csrc/synth.cpp",
         "sharding": "single GPU" if n_gpus == 1 else f"whole paths LPT-partitioned over {n_gpus} GPUs + allreduce of [depth|uniq]",
         "l2_policy": "inputs larger than L2 (per-GPU steps shard >= 200 MB vs 126 MB L2); no explicit flush",
     }
+
+
+def measure_extra(cfg, world, rank, dev, steps, peak):
+    """One of the other BASELINE.json configs on this job's GPUs: steps/s, fraction of the HBM
+    roofline for the whole step, engine, and an oracle check of the result (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from pollen_b200 import sharding, synth
+
+    start, end = synth.make_spans(cfg.n_paths, cfg.n_steps, cfg.jitter_pct)
+    parts = sharding.lpt_partition(end - start, world)
+    if world == 1:
+        h, ls, le = synth.make_graph(cfg)
+    else:
+        h, ls, le = synth.make_graph(cfg, path_subset=parts[rank])
+    d_steps = torch.from_numpy(h.view(np.int32)).to(dev)
+    eng = sharding.ShardedDepth(ls, le, cfg.n_segs, dev, n_paths_global=cfg.n_paths if world > 1 else None)
+    stream = torch.cuda.current_stream(dev)
+    engine = eng.plan.autotune(d_steps, stream.cuda_stream)
+    for _ in range(3):
+        eng.run(d_steps, stream)
+    eng.status()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+        eng.run(d_steps, stream)
+    b.record(stream)
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    eng.status()
+    gd, gu = eng.results()
+    ok = None
+    if rank == 0:
+        import oracle_lib as O
+        f_steps, f_start, f_end = (h, ls, le) if world == 1 else synth.make_graph(cfg)
+        rc, od, ou = O.depth_with_uniq(f_steps, f_start, f_end, cfg.n_segs)
+        ok = rc == 0 and bool((gd == od).all()) and bool((gu == ou).all())
+    alg = 4.0 * cfg.n_steps + 8.0 * cfg.n_paths + 8.0 * cfg.n_segs
+    out = {"workload": f"{cfg.name}: {cfg.description}", "n_gpus": world, "steps": steps, "ms_per_step": ms,
+           "value": cfg.n_steps / (ms * 1e-3), "unit": UNIT, "engine": engine,
+           "whole_step_frac": alg / world / (ms * 1e-3) / 1e9 / peak, "parity_vs_oracle": ok,
+           "exchange": "none" if world == 1 else "nccl all_reduce of [depth u32 | uniq u8]"}
+    del eng, d_steps
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -169,7 +225,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="C")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = --steps")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (B, E)")
     args = ap.parse_args()
 
     from pollen_b200 import synth
@@ -208,6 +265,7 @@ def main():
     d_steps = torch.empty(n_local, dtype=torch.int32, device=dev)
     d_steps.copy_(h_steps)
     eng = sharding.ShardedDepth(ls, le, cfg.n_segs, dev, n_paths_global=cfg.n_paths if world > 1 else None)
+    engine_name = eng.plan.autotune(d_steps, torch.cuda.current_stream(dev).cuda_stream)
     exchange = "none (single GPU)" if world == 1 else "nccl all_reduce of [depth u32 | uniq u8]" if eng.compact else "nccl all_reduce of [depth u32 | uniq u32]"
     if world > 1 and cfg.n_paths <= 255 and os.environ.get("FGFA_EXCHANGE", "fused") == "fused":
         # Preferred exchange: popcount fused with a reduce-scatter/all-gather over NVLink peer
@@ -246,7 +304,8 @@ def main():
         except Exception as exc:  # symmetric memory not available: keep NCCL
             exchange += f" (fused exchange unavailable: {type(exc).__name__})"
     stream = torch.cuda.current_stream(dev)
-    launches_per_step = eng.plan.launches(True) if isinstance(eng, sharding.ShardedDepth) else 2   # kernel A + B, or A + X
+    launches_per_step = eng.plan.launches(True) if isinstance(eng, sharding.ShardedDepth) else 2   # S1-S3 + W + B2 / A + B, or A + X
+    engine_name = eng.plan.engine
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -291,20 +350,21 @@ def main():
     depth_sum = int(eng.depth.to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
     assert depth_sum == cfg.n_steps, (depth_sum, cfg.n_steps)
 
-    # ---- roofline of the dominant kernel (kernel A, the step stream) -------------------
+    # ---- roofline of the dominant kernel (kernel W of the window engine / kernel A of the stream engine) ----
     peak, peak_src = peak_hbm()
     alg_bytes = 4.0 * n_local + 8.0 * len(my_paths) + 4.0 * cfg.n_segs   # per launch, this rank (slowest rank's time)
     k_ms = float(ms_kernel.item())
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_step_stream_merged", "kernel_ms": k_ms,
+                "traffic": None, "kernel": "k_window_count" if engine_name == "window" else "k_step_stream_merged",
+                "engine": engine_name, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "whole_step_frac": (4.0 * cfg.n_steps + 8.0 * cfg.n_paths + 8.0 * cfg.n_segs) / world / (ms_per_step * 1e-3) / 1e9 / peak}
 
     roofline["frac_of_nominal_8tbs"] = achieved / 8000.0
     try:   # DRAM traffic of one kernel-A launch from the committed `ncu --set full` capture (N=1, config C)
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(f"{cfg.name}:{world}")
+            t = json.load(f).get(f"{cfg.name}:{world}:{engine_name}")
         if t:
             roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
             roofline["traffic_source"] = t["source"]
@@ -340,7 +400,7 @@ def main():
              "stream_kernel_ms": k_ms, "per_step_rank0": step_stats}
 
     # ---- end to end: host buffers in, host results out ---------------------------------
-    e2e_steps = max(1, args.e2e_steps)
+    e2e_steps = max(1, args.e2e_steps or args.steps)
     if world == 1:
         # the drop-in C-ABI call on host buffers (allocates, uploads in pipelined groups,
         # runs, downloads, widens to u64) -- what a caller of the reference's op would use
@@ -387,6 +447,41 @@ def main():
 
     clocks = sampler.stop() if sampler else None
 
+    # ---- parity against the oracle, in the driver-visible run: the whole graph, every segment ----
+    eng.run(d_steps, stream)
+    eng.status()
+    g_depth, g_uniq = eng.results()
+    parity = None
+    if rank == 0:
+        import oracle_lib as O
+        if world == 1:
+            f_steps, f_start, f_end = h_steps_np, ls, le
+        else:
+            f_steps, f_start, f_end = synth.make_graph(cfg)
+        rc, od, ou = O.depth_with_uniq(f_steps, f_start, f_end, cfg.n_segs)
+        ok = rc == 0 and bool((g_depth == od).all()) and bool((g_uniq == ou).all())
+        parity = {"vs_oracle": ok, "n_gpus": world, "engine": engine_name,
+                  "checked": f"depth and depth.uniq of all {cfg.n_segs} segments against the C oracle over the whole graph"}
+        if world > 1:
+            del f_steps
+    flag = torch.tensor([0 if (parity is None or parity["vs_oracle"]) else 1], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()):
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "error": "PARITY MISMATCH against the oracle", "parity": parity}))
+        raise SystemExit(3)
+
+    # ---- the other BASELINE configs, outside the main timed region ----------------------
+    extra = None
+    if not args.no_extra and cfg.name == "C":
+        extra = {}
+        del d_steps, h_steps
+        torch.cuda.empty_cache()
+        names = ["B", "E"] if world == 1 else (["E"] if world == 8 else [])
+        for name in names:
+            extra[f"{name}@{world}"] = measure_extra(synth.CONFIGS[name], world, rank, dev, max(5, args.steps), peak)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -401,7 +496,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload_config(cfg, world, exchange), "roofline": roofline, "split": split, "cpu_baseline": cpu, "e2e": e2e,
+            "config": workload_config(cfg, world), "exchange": exchange, "engine": engine_name, "roofline": roofline, "split": split, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "extra_configs": extra,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }))
     if world > 1:

@@ -128,6 +128,53 @@ int fgfa_exchange_uniq_depth(int n_ranks, int rank, const void* const* bitmaps, 
                              uint64_t off_partial, uint64_t off_final_depth, uint64_t off_final_uniq,
                              void* cuda_stream);
 
+/* ---- multi-GPU, one process driving N devices ------------------------------------------
+ * The reference's host is one compiled process (flatgfa/src/cli/main.rs:57-188, cmds.rs:234-245), so
+ * this is the form a Rust `fgfa --gpus N` binds.  Whole paths are partitioned over the devices by step
+ * count (longest first onto the least loaded device; `Path::step_count`, flatgfa.rs:114-118): depth is a
+ * sum over steps and uniq a sum over paths of indicator vectors (depth.rs:25-35), so both shard exactly
+ * as long as no path is split.  Every device counts its packed shard with a depth plan; the partial
+ * [depth | uniq] arrays are combined by
+ *   FGFA_EXCHANGE_NCCL  one ncclAllReduce(sum) per device inside one NCCL group.  uniq travels as u8
+ *                       (four to a word) when the graph has <= 255 paths.  libnccl.so.2 is loaded on
+ *                       first use; this library has no link-time dependency on it.
+ *   FGFA_EXCHANGE_PEER  kernel X (fgfa_exchange_uniq_depth): popcount fused with a reduce-scatter /
+ *                       all-gather over peer-mapped memory, ordered with CUDA events.  <= 255 paths,
+ *                       devices must be able to map each other's memory.
+ * create() owns the communicators, streams, plans and buffers; destroy() releases them (the
+ * init / destroy pair SURVEY.md section 8b asks for).  After run() every device holds the complete
+ * result.  Handles are not thread-safe; all calls return FGFA_OK or a negative code. */
+typedef struct fgfa_depth_multi fgfa_depth_multi_t;
+enum { FGFA_EXCHANGE_NCCL = 0, FGFA_EXCHANGE_PEER = 1 };
+/* devices: n_devices CUDA ordinals (distinct for NCCL).  h_span_start/end: the whole graph's spans. */
+int fgfa_depth_multi_create(fgfa_depth_multi_t** out, const int* devices, int n_devices,
+                            const uint32_t* h_span_start, const uint32_t* h_span_end, uint32_t n_paths,
+                            uint32_t n_segs, uint64_t n_steps, int exchange);
+void fgfa_depth_multi_destroy(fgfa_depth_multi_t* m);
+/* path_device[p] = index (into `devices`) of the device that owns path p; device_steps[i] = steps on
+ * device i.  Either may be NULL. */
+int fgfa_depth_multi_partition(const fgfa_depth_multi_t* m, uint32_t* path_device, uint64_t* device_steps);
+/* Make the shards resident: every path's steps go to its device, packed back to back in ascending
+ * path order (asynchronous copies; pin h_steps for full PCIe speed). */
+int fgfa_depth_multi_upload(fgfa_depth_multi_t* m, const uint32_t* h_steps);
+/* Device i's shard buffer, for callers that fill it themselves (then no upload() is needed). */
+int fgfa_depth_multi_device_steps(fgfa_depth_multi_t* m, int index, uint32_t** d_steps, uint64_t* n_steps);
+/* Enqueue one query on all devices: zero, count, exchange.  with_uniq = 0 is seg_depth (NCCL form). */
+int fgfa_depth_multi_run(fgfa_depth_multi_t* m, int with_uniq);
+/* Wait for all devices; FGFA_ERR_SEG_OOB if any shard saw a segment id >= n_segs. */
+int fgfa_depth_multi_sync(fgfa_depth_multi_t* m);
+/* sync + copy the result (device 0's replica) out as u64 counters; uniq_out may be NULL. */
+int fgfa_depth_multi_download(fgfa_depth_multi_t* m, uint64_t* depth_out, uint64_t* uniq_out);
+/* upload + run + download. */
+int fgfa_depth_multi_run_host(fgfa_depth_multi_t* m, const uint32_t* h_steps, uint64_t* depth_out, uint64_t* uniq_out);
+/* Device i's replica of the result: n_segs u32 depths; uniq as u8 (uniq_bytes = 1) or u32 (4). */
+int fgfa_depth_multi_result_device(fgfa_depth_multi_t* m, int index, const uint32_t** d_depth, const void** d_uniq,
+                                   int* uniq_bytes);
+const char* fgfa_depth_multi_last_error(void);
+/* The partition alone (pure host code): path_part[p] = part (0..n_parts-1) that owns path p. */
+int fgfa_lpt_partition(const uint32_t* h_span_start, const uint32_t* h_span_end, uint32_t n_paths, int n_parts,
+                       uint32_t* path_part);
+
 /* Width of the uniq counters the plan's runs write to d_uniq: 4 (default, u32) or 1 (u8;
  * only for plans of <= 255 paths, since uniq <= n_paths).  The narrow form exists for the
  * multi-GPU exchange: [depth u32 | uniq u8] is 25 MB instead of 40 MB at 5 M segments, and

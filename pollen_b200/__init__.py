@@ -10,6 +10,7 @@ the built library or without a CUDA device raises.
 from .binding import (  # noqa: F401
     DepthError,
     DepthPlan,
+    MultiDepth,
     FlatBED,
     FlatGFA,
     SegDepth,
@@ -28,6 +29,7 @@ from .binding import (  # noqa: F401
 __all__ = [
     "DepthError",
     "DepthPlan",
+    "MultiDepth",
     "FlatBED",
     "FlatGFA",
     "SegDepth",

@@ -92,6 +92,18 @@ EXPORTS = {
     "fgfa_depth_plan_run_stream_only": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_exchange_uniq_depth": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "fgfa_depth_plan_set_uniq_width": (C.c_int, [C.c_void_p, C.c_int]),
+    "fgfa_depth_multi_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]),
+    "fgfa_depth_multi_destroy": (None, [C.c_void_p]),
+    "fgfa_depth_multi_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_multi_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fgfa_depth_multi_device_steps": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "fgfa_depth_multi_run": (C.c_int, [C.c_void_p, C.c_int]),
+    "fgfa_depth_multi_sync": (C.c_int, [C.c_void_p]),
+    "fgfa_depth_multi_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_multi_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgfa_depth_multi_result_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "fgfa_depth_multi_last_error": (C.c_char_p, []),
+    "fgfa_lpt_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]),
     "fgfa_depth_plan_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
     "fgfa_depth_plan_engine": (C.c_int, [C.c_void_p]),
     "fgfa_depth_plan_autotune": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -479,6 +491,81 @@ def exchange_uniq_depth(n_ranks, rank, bitmaps, rows, partial_depths, final_dept
     _check(lib().fgfa_exchange_uniq_depth(n_ranks, rank, P(*bitmaps), r.ctypes.data, P(*partial_depths),
                                           P(*final_depths), P(*final_uniqs), n_segs, multicast_base or None,
                                           off_partial, off_final_depth, off_final_uniq, stream or None))
+
+
+def lpt_partition_c(span_start, span_end, n_parts: int) -> np.ndarray:
+    """fgfa_lpt_partition: part index of every path (the C++ partition the multi-GPU ABI uses)."""
+    s, e = _u32(span_start), _u32(span_end)
+    out = np.empty(s.size, np.uint32)
+    _check(lib().fgfa_lpt_partition(s.ctypes.data, e.ctypes.data, int(s.size), int(n_parts), out.ctypes.data))
+    return out
+
+
+class MultiDepth:
+    """fgfa_depth_multi_*: one process driving several GPUs (whole paths per device, partial
+    [depth | uniq] combined by NCCL or by kernel X over peer memory)."""
+
+    EXCHANGES = {"nccl": 0, "peer": 1}
+
+    def __init__(self, devices, span_start, span_end, n_segs: int, n_steps: int, exchange: str = "nccl"):
+        self.span_start, self.span_end = _u32(span_start), _u32(span_end)
+        self.n_segs, self.n_steps = int(n_segs), int(n_steps)
+        self.devices = np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        rc = lib().fgfa_depth_multi_create(C.byref(h), self.devices.ctypes.data, int(self.devices.size),
+                                           self.span_start.ctypes.data, self.span_end.ctypes.data,
+                                           int(self.span_start.size), self.n_segs, self.n_steps, self.EXCHANGES[exchange])
+        if rc:
+            raise DepthError(rc, lib().fgfa_depth_multi_last_error().decode())
+        self._h = h
+
+    def _ck(self, rc):
+        if rc:
+            raise DepthError(rc, lib().fgfa_depth_multi_last_error().decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().fgfa_depth_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def partition(self):
+        owner = np.empty(self.span_start.size, np.uint32)
+        steps = np.empty(self.devices.size, np.uint64)
+        self._ck(lib().fgfa_depth_multi_partition(self._h, owner.ctypes.data, steps.ctypes.data))
+        return owner, steps
+
+    def upload(self, h_steps) -> None:
+        h = _u32(h_steps)
+        self._ck(lib().fgfa_depth_multi_upload(self._h, h.ctypes.data))
+
+    def run(self, with_uniq: bool = True) -> None:
+        self._ck(lib().fgfa_depth_multi_run(self._h, 1 if with_uniq else 0))
+
+    def sync(self) -> None:
+        self._ck(lib().fgfa_depth_multi_sync(self._h))
+
+    def download(self, with_uniq: bool = True):
+        d = np.empty(self.n_segs, np.uint64)
+        u = np.empty(self.n_segs, np.uint64) if with_uniq else None
+        self._ck(lib().fgfa_depth_multi_download(self._h, d.ctypes.data, u.ctypes.data if with_uniq else None))
+        return d, u
+
+    def run_host(self, h_steps, with_uniq: bool = True):
+        h = _u32(h_steps)
+        d = np.empty(self.n_segs, np.uint64)
+        u = np.empty(self.n_segs, np.uint64) if with_uniq else None
+        self._ck(lib().fgfa_depth_multi_run_host(self._h, h.ctypes.data, d.ctypes.data, u.ctypes.data if with_uniq else None))
+        return d, u
+
+    def run_host_ptr(self, h_ptr: int, d_ptr: int, u_ptr: int) -> None:
+        """Raw-pointer form (pinned torch tensors / numpy buffers owned by the caller)."""
+        self._ck(lib().fgfa_depth_multi_run_host(self._h, h_ptr, d_ptr, u_ptr or None))
 
 
 class DepthPlan:

@@ -44,8 +44,13 @@ int text_out(const std::string& s, char** out, size_t* out_len) {
     *out_len = s.size();
     return FGFA_OK;
 }
+// The FGFA_ERR_* a C entry point returns for an exception: the code the device ABI reported when the
+// exception carries one (so flatgfa_path_depth / _interval_depth / _window_depth / _bed_depth agree with
+// flatgfa_seg_depth), FGFA_ERR_INVALID_ARG for host-side complaints (unknown path, zero window ...).
 int code_of(const std::exception& e) {
     g_err = e.what();
+    if (const auto* fe = dynamic_cast<const flatgfa::Error*>(&e))
+        if (fe->code) return fe->code;
     if (std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "no usable CUDA device")) return FGFA_ERR_NO_DEVICE;
     return FGFA_ERR_INVALID_ARG;
 }
@@ -133,23 +138,10 @@ bool flatgfa_get_step(flatgfa_t gfa, uintptr_t path_index, uintptr_t step_index,
 int flatgfa_seg_depth(flatgfa_t gfa, uint64_t* depth, uint64_t* uniq) {
     if (!gfa || (!depth && gfa->gfa.segs.len())) return FGFA_ERR_INVALID_ARG;
     const auto& g = gfa->gfa;
-    if (g.segs.len() > 0x7FFFFFFFull || g.paths.len() > 0xFFFFFFFFull || g.steps.len() > 0xFFFFFFFFull)
-        return FGFA_ERR_TOO_LARGE;
-    const uint32_t n_paths = (uint32_t)g.paths.len();
-    std::vector<uint32_t> s(n_paths), e(n_paths);
-    for (uint32_t p = 0; p < n_paths; ++p) {
-        s[p] = g.paths.data[p].steps.start;
-        e[p] = g.paths.data[p].steps.end;
-    }
-    const uint32_t* steps = reinterpret_cast<const uint32_t*>(g.steps.data);
-    std::vector<uint32_t> aligned;
-    if (reinterpret_cast<uintptr_t>(steps) & 3u) {
-        aligned.resize(g.steps.len());
-        std::memcpy(aligned.data(), g.steps.data, g.steps.len() * 4);
-        steps = aligned.data();
-    }
-    int rc = fgfa_seg_depth_with_uniq_steps(steps, g.steps.len(), s.data(), e.data(), n_paths,
-                                            (uint32_t)g.segs.len(), depth, uniq);
+    flatgfa::ops::depth::PoolArrays a;
+    int rc = flatgfa::ops::depth::pool_arrays_of(g, &a);
+    if (!rc)
+        rc = fgfa_seg_depth_with_uniq_steps(a.steps, a.n_steps, a.start.data(), a.end.data(), a.n_paths, a.n_segs, depth, uniq);
     if (rc) {
         g_err = fgfa_strerror(rc);
         const char* detail = fgfa_last_error();
@@ -182,8 +174,7 @@ int flatgfa_path_depth(flatgfa_t gfa, const uint32_t* path_ids, uint32_t n, uint
         for (uint32_t i = 0; i < n; ++i) { lengths[i] = ld.first[i]; mean_depths[i] = ld.second[i]; }
         return FGFA_OK;
     } catch (const std::exception& e) {
-        g_err = e.what();
-        return std::strstr(e.what(), "no CUDA device") ? FGFA_ERR_NO_DEVICE : FGFA_ERR_CUDA;
+        return code_of(e);
     }
 }
 

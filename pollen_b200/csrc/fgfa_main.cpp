@@ -4,6 +4,8 @@
 // flatgfa/src/cli/cmds.rs:217-232 `depth` options, main.rs:87-138 input loading and
 // dispatch, main.rs:190-213 `dump`):
 //   fgfa [-i FLATGFA | -I GFA | < GFA] depth -d          node-depth table on stdout
+//   fgfa --gpus N [...] depth -d                         the same table, computed on N GPUs of this box
+//                                                        (an addition: the reference has no devices)
 //   fgfa [-i FLATGFA | -I GFA | < GFA] depth [-r PATH]   path-depth table (cmds.rs:256-283)
 //   fgfa [-i FLATGFA | -I GFA | < GFA] depth -b BED      interval depth table (cmds.rs:246-255)
 //   fgfa [-i FLATGFA | -I GFA | < GFA] window-depth PATH SIZE   (cmds.rs:477-496)
@@ -31,6 +33,7 @@ struct Args {
     std::string input, input_gfa, output, output_gfa;   // -i -I -o -O
     bool mutate = false;                                // -m
     size_t prealloc_factor = 32;                        // -p
+    int gpus = 1;                                       // --gpus (not in the reference)
     std::string command;
     // depth (cmds.rs:217-232)
     bool seg_depth = false;                             // -d / --graph-depth-table
@@ -44,7 +47,7 @@ int usage(const char* msg) {
     if (msg) std::fprintf(stderr, "%s\n", msg);
     std::fprintf(stderr,
                  "Usage: fgfa [-i <input>] [-I <input-gfa>] [-o <output>] [-O <output-gfa>] [-m] "
-                 "[-p <prealloc-factor>] [<command>] [<args>]\n\n"
+                 "[-p <prealloc-factor>] [--gpus <n>] [<command>] [<args>]\n\n"
                  "Convert between GFA text and FlatGFA binary formats.\n\n"
                  "Commands:\n  depth             compute depth: the number of times paths cross a node\n"
                  "                    -d, --graph-depth-table  compute node depth instead of path depth\n"
@@ -72,7 +75,22 @@ int main(int argc, char** argv) {
         else if (t == "-o") { if (!take(i, argc, argv, a.output)) return usage("No value provided for option '-o'."); }
         else if (t == "-O") { if (!take(i, argc, argv, a.output_gfa)) return usage("No value provided for option '-O'."); }
         else if (t == "-m") a.mutate = true;
-        else if (t == "-p") { std::string v; if (!take(i, argc, argv, v)) return usage("No value provided for option '-p'."); a.prealloc_factor = std::stoul(v); }
+        else if (t == "-p") {
+            std::string v;
+            if (!take(i, argc, argv, v)) return usage("No value provided for option '-p'.");
+            char* endp = nullptr;
+            const unsigned long long f = std::strtoull(v.c_str(), &endp, 10);
+            if (v.empty() || *endp || v[0] == '-') return usage("Error parsing option '-p': not a number");
+            a.prealloc_factor = (size_t)f;
+        }
+        else if (t == "--gpus") {
+            std::string v;
+            if (!take(i, argc, argv, v)) return usage("No value provided for option '--gpus'.");
+            char* endp = nullptr;
+            const long g = std::strtol(v.c_str(), &endp, 10);
+            if (v.empty() || *endp || g < 1 || g > 16) return usage("Error parsing option '--gpus': expected 1..16");
+            a.gpus = (int)g;
+        }
         else if (t == "--help" || t == "help") { usage(nullptr); return 0; }
         else if (!t.empty() && t[0] == '-') return usage(("Unrecognized argument: " + t).c_str());
         else { a.command = t; ++i; break; }
@@ -162,7 +180,7 @@ int main(int argc, char** argv) {
                 flatgfa::ops::depth::PathDepth{gfa, std::move(ld.first), std::move(ld.second), ids}.print();
                 return 0;
             }
-            auto du = flatgfa::ops::depth::seg_depth_with_uniq(gfa);          // cmds.rs:239
+            auto du = flatgfa::ops::depth::seg_depth_with_uniq(gfa, a.gpus);  // cmds.rs:239
             flatgfa::ops::depth::SegDepth{gfa, std::move(du.first), std::move(du.second)}.print();  // cmds.rs:240-245
             return 0;
         }

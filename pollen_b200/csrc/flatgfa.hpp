@@ -20,6 +20,10 @@ namespace flatgfa {
 // C ABI / CLI turn the exception into an error code / message.
 struct Error : std::runtime_error {
     using std::runtime_error::runtime_error;
+    // FGFA_ERR_* of a failed device call (0 = a host-side error without a code); the C entry points
+    // hand it back unchanged so that all of them report the same code for the same failure
+    Error(const std::string& what, int code_) : std::runtime_error(what), code(code_) {}
+    int code = 0;
 };
 
 #pragma pack(push, 1)

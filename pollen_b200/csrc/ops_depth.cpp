@@ -309,25 +309,11 @@ static int depth_of_image(const void* bytes, size_t len, uint64_t* depth_out, ui
         case flatgfa::file::kViewBadMagic: return FGFA_ERR_BAD_MAGIC;
         default: return FGFA_ERR_TRUNCATED;
     }
-    if (g.segs.len() > 0x7FFFFFFFull || g.paths.len() > 0xFFFFFFFFull || g.steps.len() > 0xFFFFFFFFull)
-        return FGFA_ERR_TOO_LARGE;
-    const uint32_t n_paths = (uint32_t)g.paths.len();
-    std::vector<uint32_t> s(n_paths), e(n_paths);
-    for (uint32_t p = 0; p < n_paths; ++p) {   // flatgfa.rs:99-112: Path.steps
-        s[p] = g.paths.data[p].steps.start;
-        e[p] = g.paths.data[p].steps.end;
-    }
-    // The steps pool sits at an arbitrary byte offset of the image; a
-    // 4-byte-aligned host pointer is all the upload needs, so realign only if necessary.
-    const uint32_t* steps = reinterpret_cast<const uint32_t*>(g.steps.data);
-    std::vector<uint32_t> aligned;
-    if (reinterpret_cast<uintptr_t>(steps) & 3u) {
-        aligned.resize(g.steps.len());
-        std::memcpy(aligned.data(), g.steps.data, g.steps.len() * 4);
-        steps = aligned.data();
-    }
-    return fgfa_seg_depth_with_uniq_steps(steps, g.steps.len(), s.data(), e.data(), n_paths,
-                                          (uint32_t)g.segs.len(), depth_out, uniq_out);
+    flatgfa::ops::depth::PoolArrays a;
+    const int rc = flatgfa::ops::depth::pool_arrays_of(g, &a);
+    if (rc) return rc;
+    return fgfa_seg_depth_with_uniq_steps(a.steps, a.n_steps, a.start.data(), a.end.data(), a.n_paths, a.n_segs,
+                                          depth_out, uniq_out);
 }
 
 int fgfa_seg_depth_with_uniq(const void* bytes, size_t len, uint64_t* depth_out, uint64_t* uniq_out) {
@@ -461,31 +447,19 @@ namespace depth {
 
 namespace {
 int run_on(const FlatGFA& gfa, std::vector<uint64_t>& d, std::vector<uint64_t>* u) {
-    if (gfa.segs.len() > 0x7FFFFFFFull || gfa.paths.len() > 0xFFFFFFFFull || gfa.steps.len() > 0xFFFFFFFFull)
-        return FGFA_ERR_TOO_LARGE;
-    const uint32_t n_paths = (uint32_t)gfa.paths.len();
-    std::vector<uint32_t> s(n_paths), e(n_paths);
-    for (uint32_t p = 0; p < n_paths; ++p) {
-        s[p] = gfa.paths.data[p].steps.start;
-        e[p] = gfa.paths.data[p].steps.end;
-    }
-    const uint32_t* steps = reinterpret_cast<const uint32_t*>(gfa.steps.data);
-    std::vector<uint32_t> aligned;
-    if (reinterpret_cast<uintptr_t>(steps) & 3u) {
-        aligned.resize(gfa.steps.len());
-        std::memcpy(aligned.data(), gfa.steps.data, gfa.steps.len() * 4);
-        steps = aligned.data();
-    }
+    PoolArrays a;
+    const int rc = pool_arrays_of(gfa, &a);
+    if (rc) return rc;
     d.assign(gfa.segs.len(), 0);
     if (u) u->assign(gfa.segs.len(), 0);
-    return fgfa_seg_depth_with_uniq_steps(steps, gfa.steps.len(), s.data(), e.data(), n_paths,
-                                          (uint32_t)gfa.segs.len(), d.data(), u ? u->data() : nullptr);
+    return fgfa_seg_depth_with_uniq_steps(a.steps, a.n_steps, a.start.data(), a.end.data(), a.n_paths, a.n_segs,
+                                          d.data(), u ? u->data() : nullptr);
 }
 [[noreturn]] void raise(int rc) {
     std::string m = fgfa_strerror(rc);
     const char* detail = fgfa_last_error();
     if (detail && *detail) m += std::string(": ") + detail;
-    throw Error(m);
+    throw Error(m, rc);
 }
 }  // namespace
 
@@ -493,6 +467,47 @@ std::pair<std::vector<uint64_t>, std::vector<uint64_t>> seg_depth_with_uniq(cons
     std::vector<uint64_t> d, u;
     int rc = run_on(gfa, d, &u);
     if (rc) raise(rc);
+    return {std::move(d), std::move(u)};
+}
+
+int pool_arrays_of(const FlatGFA& gfa, PoolArrays* a) {
+    if (gfa.segs.len() > 0x7FFFFFFFull || gfa.paths.len() > 0xFFFFFFFFull || gfa.steps.len() > 0xFFFFFFFFull)
+        return FGFA_ERR_TOO_LARGE;
+    a->n_paths = (uint32_t)gfa.paths.len();
+    a->n_segs = (uint32_t)gfa.segs.len();
+    a->n_steps = gfa.steps.len();
+    a->start.resize(a->n_paths);
+    a->end.resize(a->n_paths);
+    for (uint32_t p = 0; p < a->n_paths; ++p) {   // flatgfa.rs:99-112: Path.steps
+        a->start[p] = gfa.paths.data[p].steps.start;
+        a->end[p] = gfa.paths.data[p].steps.end;
+    }
+    a->steps = reinterpret_cast<const uint32_t*>(gfa.steps.data);
+    if (reinterpret_cast<uintptr_t>(a->steps) & 3u) {
+        a->realigned.resize(gfa.steps.len());
+        std::memcpy(a->realigned.data(), gfa.steps.data, gfa.steps.len() * 4);
+        a->steps = a->realigned.data();
+    }
+    return FGFA_OK;
+}
+
+std::pair<std::vector<uint64_t>, std::vector<uint64_t>> seg_depth_with_uniq(const FlatGFA& gfa, int n_gpus) {
+    n_gpus = std::min(n_gpus, fgfa_device_count());
+    if (n_gpus <= 1) return seg_depth_with_uniq(gfa);
+    PoolArrays a;
+    int rc = pool_arrays_of(gfa, &a);
+    if (rc) raise(rc);
+    std::vector<int> devices((size_t)n_gpus);
+    for (int i = 0; i < n_gpus; ++i) devices[i] = i;
+    fgfa_depth_multi_t* m = nullptr;
+    rc = fgfa_depth_multi_create(&m, devices.data(), n_gpus, a.start.data(), a.end.data(), a.n_paths, a.n_segs, a.n_steps,
+                                 FGFA_EXCHANGE_NCCL);
+    if (rc) throw Error(std::string(fgfa_strerror(rc)) + ": " + fgfa_depth_multi_last_error(), rc);
+    std::vector<uint64_t> d(a.n_segs), u(a.n_segs);
+    rc = fgfa_depth_multi_run_host(m, a.steps, d.data(), u.data());
+    const std::string detail = rc ? fgfa_depth_multi_last_error() : "";
+    fgfa_depth_multi_destroy(m);
+    if (rc) throw Error(std::string(fgfa_strerror(rc)) + ": " + detail, rc);
     return {std::move(d), std::move(u)};
 }
 

@@ -22,6 +22,24 @@ std::pair<std::vector<uint64_t>, std::vector<uint64_t>> seg_depth_with_uniq(cons
 // depth.rs:45-56.
 std::vector<uint64_t> seg_depth(const FlatGFA& gfa);
 
+// The same op on `n_gpus` devices of this box (whole paths partitioned by step count, partial
+// arrays combined with one NCCL all-reduce; fgfa_depth_multi_* in fgfa_depth.h).  n_gpus <= 1 is
+// seg_depth_with_uniq(gfa); more than the box has is clamped.
+std::pair<std::vector<uint64_t>, std::vector<uint64_t>> seg_depth_with_uniq(const FlatGFA& gfa, int n_gpus);
+
+// What every host entry point hands to the device ABI: the per-path `steps` spans
+// (flatgfa.rs:99-112), a 4-byte-aligned view of the steps pool (the pool sits at an arbitrary byte
+// offset of a .flatgfa image; it is copied only when misaligned) and the counts.
+struct PoolArrays {
+    std::vector<uint32_t> start, end;
+    const uint32_t* steps = nullptr;
+    uint32_t n_paths = 0, n_segs = 0;
+    uint64_t n_steps = 0;
+    std::vector<uint32_t> realigned;    // backing store of `steps` when the pool was misaligned
+};
+// FGFA_OK, or FGFA_ERR_TOO_LARGE when a count does not fit the format's u32 ids (pool.rs:9-11).
+int pool_arrays_of(const FlatGFA& gfa, PoolArrays* out);
+
 // depth.rs:61-82: the odgi-style TSV table.
 struct SegDepth {
     const FlatGFA& gfa;

@@ -14,7 +14,7 @@ namespace {
     std::string m = fgfa_strerror(rc);
     const char* detail = fgfa_last_error();
     if (detail && *detail) m += std::string(": ") + detail;
-    throw Error(m);
+    throw Error(m, rc);
 }
 
 struct Arrays {

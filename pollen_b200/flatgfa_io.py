@@ -10,10 +10,12 @@ MAGIC = 0xB1011054
 
 
 def build_image(steps: np.ndarray, span_start, span_end, n_segs: int, header: bytes = b"VN:Z:1.0",
-                seg_names=None, slack: int = 0) -> np.ndarray:
+                seg_names=None, slack: int = 0, record_lines: bool = True) -> np.ndarray:
     """Returns the file image as a uint8 array.  Segments are named 1..n_segs (or
     ``seg_names``) with 1-byte sequences; paths are named p0, p1, ...; no links.
-    ``slack`` extra capacity slots are left in every pool (capacity > len)."""
+    ``slack`` extra capacity slots are left in every pool (capacity > len).  ``record_lines=False``
+    leaves line_order empty, like the graphs the reference's extract / chop build (they never call
+    record_line): printing such a graph takes print.rs's normalised branch."""
     steps = np.ascontiguousarray(steps, dtype=np.uint32)
     span_start = np.asarray(span_start, dtype=np.uint32)
     span_end = np.asarray(span_end, dtype=np.uint32)
@@ -37,6 +39,8 @@ def build_image(steps: np.ndarray, span_start, span_end, n_segs: int, header: by
         paths["st1"] = span_end
     line_order = np.concatenate([
         np.full(1 if header else 0, 0, np.uint8), np.full(n_segs, 1, np.uint8), np.full(n_paths, 2, np.uint8)])
+    if not record_lines:
+        line_order = np.zeros(0, np.uint8)
 
     pools = [
         (np.frombuffer(header, dtype=np.uint8), 1),

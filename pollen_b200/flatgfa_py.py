@@ -304,6 +304,10 @@ class FlatGFA:
 
     def __str__(self) -> str:                                  # print.rs:100-127 (original line order)
         v = self._v
+        if len(v.line_order) == 0:
+            # print.rs:129-153 `write_normalized`: graphs built by ops that never call record_line
+            # (extract, chop ...) have an empty line_order and are printed header, segments, paths, links
+            return self._h.format_gfa().decode()
         out = []
         it = {1: iter(self.segments), 2: iter(self.paths), 3: iter(self.links)}
         for kind in v.line_order:

@@ -131,6 +131,22 @@ def test_slice(gfa):
     assert len(list(path[2:])) == len(path) - 2
 
 
+def test_graph_without_recorded_lines_prints_normalized(tmp_path):
+    """print.rs:129-153: a graph whose line_order is empty (what the reference's extract / chop
+    produce) is printed header, segments, paths, links -- str() and write_gfa() must not come out empty."""
+    from pollen_b200 import flatgfa_io
+
+    steps = np.array([0, 2, 5, 2], np.uint32)
+    for record in (True, False):
+        p = tmp_path / f"g{int(record)}.flatgfa"
+        flatgfa_io.write_flatgfa(str(p), steps, [0, 2], [2, 4], 3, record_lines=record)
+    a, b = flatgfa.load(str(tmp_path / "g1.flatgfa")), flatgfa.load(str(tmp_path / "g0.flatgfa"))
+    want = "H\tVN:Z:1.0\nS\t1\tA\nS\t2\tC\nS\t3\tG\nP\tp0\t1+,2+\t*\nP\tp1\t3-,2+\t*\n"
+    assert str(a) == want and str(b) == want
+    b.write_gfa(str(tmp_path / "out.gfa"))
+    assert (tmp_path / "out.gfa").read_text() == want
+
+
 def test_round_trips_every_golden_graph(golden):
     """str(graph) reproduces the GFA text for every fixture whose lines our writer covers
     (H/S/P/L, original order: print.rs:100-127)."""
