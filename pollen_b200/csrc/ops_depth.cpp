@@ -33,6 +33,11 @@ struct Workspace {
     void* aux2 = nullptr;       size_t aux2_cap = 0;      // bytes (interval depth: intervals, scratch, results)
     cudaStream_t copy = nullptr, compute = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // pinned ring for callers whose steps live in pageable memory (an mmapped .flatgfa, the
+    // reference's normal case: memfile.rs:7-10): a group is copied into a slot by host threads
+    // while the previous group's slot is on its way over PCIe
+    uint32_t* ring[2] = {nullptr, nullptr};  size_t ring_cap = 0;   // elements per slot
+    cudaEvent_t ring_free[2] = {nullptr, nullptr};
     fgfa_depth_plan_t* plan = nullptr;
     uint64_t plan_key[4] = {0, 0, 0, 0};
     std::vector<uint32_t> plan_start, plan_end;   // the cached plan's span table (exact comparison)
@@ -48,6 +53,9 @@ struct Workspace {
         cudaFree(aux); aux = nullptr; aux_cap = 0;
         cudaFree(aux2); aux2 = nullptr; aux2_cap = 0;
         for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : ring_free) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& r : ring) { if (r) cudaFreeHost(r); r = nullptr; }
+        ring_cap = 0;
         if (copy) cudaStreamDestroy(copy);
         if (compute) cudaStreamDestroy(compute);
         copy = compute = nullptr;
@@ -118,6 +126,8 @@ int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, size_t aux
         CUH(cudaStreamCreateWithFlags(&w.compute, cudaStreamNonBlocking));
         CUH(cudaEventCreateWithFlags(&w.ev[0], cudaEventDisableTiming));
         CUH(cudaEventCreateWithFlags(&w.ev[1], cudaEventDisableTiming));
+        CUH(cudaEventCreateWithFlags(&w.ring_free[0], cudaEventDisableTiming));
+        CUH(cudaEventCreateWithFlags(&w.ring_free[1], cudaEventDisableTiming));
         w.device = dev;
     }
     const size_t need_steps = std::max<size_t>((size_t)n_steps, 4);
@@ -144,6 +154,27 @@ int ensure_workspace(Workspace& w, uint64_t n_steps, uint32_t n_segs, size_t aux
         w.aux_cap = aux_bytes;
     }
     return FGFA_OK;
+}
+
+// Is this host pointer page-locked (cudaMallocHost / cudaHostRegister)?  Pageable memory is staged
+// through the workspace's pinned ring instead of being handed to cudaMemcpyAsync directly.
+bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void parallel_copy(uint32_t* dst, const uint32_t* src, size_t n) {
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (n < (1u << 20) || hw == 1) { std::memcpy(dst, src, n * 4); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + hw - 1) / hw;
+    for (unsigned t = 0; t < hw; ++t) {
+        const size_t a = t * per, b = std::min(n, a + per);
+        if (a >= b) break;
+        th.emplace_back([=] { std::memcpy(dst + a, src + a, (b - a) * 4); });
+    }
+    for (auto& t : th) t.join();
 }
 
 void widen(const uint32_t* src, uint64_t* dst, size_t n) {
@@ -199,6 +230,24 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
     bool monotone = true;
     for (uint32_t p = 1; p < n_paths && monotone; ++p) monotone = h_span_start[p] >= h_span_end[p - 1];
     if (monotone && n_paths) {
+        const bool pinned = n_steps == 0 || host_pointer_is_pinned(h_steps);
+        if (!pinned) {                    // size the ring for the largest upload group
+            uint64_t largest = 0;
+            for (uint32_t lo = 0; lo < n_paths;) {
+                uint32_t hi = lo;
+                uint64_t acc = 0;
+                while (hi < n_paths && (acc == 0 || acc < kUploadGroupSteps)) { acc += (uint64_t)h_span_end[hi] - h_span_start[hi]; ++hi; }
+                largest = std::max<uint64_t>(largest, (uint64_t)h_span_end[hi - 1] - h_span_start[lo]);
+                lo = hi;
+            }
+            if (W.ring_cap < largest) {
+                for (auto& r : W.ring) { if (r) cudaFreeHost(r); r = nullptr; }
+                W.ring_cap = 0;
+                CUH(cudaMallocHost(&W.ring[0], std::max<size_t>((size_t)largest * 4, 16)));
+                CUH(cudaMallocHost(&W.ring[1], std::max<size_t>((size_t)largest * 4, 16)));
+                W.ring_cap = (size_t)largest;
+            }
+        }
         uint32_t lo = 0;
         int slot = 0;
         while (lo < n_paths) {
@@ -209,8 +258,14 @@ int fgfa_seg_depth_with_uniq_steps(const uint32_t* h_steps, uint64_t n_steps,
                 ++hi;
             }
             const uint64_t a = h_span_start[lo], b = h_span_end[hi - 1];
-            if (b > a)
+            if (b > a && pinned) {
                 CUH(cudaMemcpyAsync(W.steps + a, h_steps + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, W.copy));
+            } else if (b > a) {
+                CUH(cudaEventSynchronize(W.ring_free[slot]));          // the slot's previous upload has left it
+                parallel_copy(W.ring[slot], h_steps + a, (size_t)(b - a));
+                CUH(cudaMemcpyAsync(W.steps + a, W.ring[slot], (size_t)(b - a) * 4, cudaMemcpyHostToDevice, W.copy));
+                CUH(cudaEventRecord(W.ring_free[slot], W.copy));
+            }
             CUH(cudaEventRecord(W.ev[slot], W.copy));
             CUH(cudaStreamWaitEvent(W.compute, W.ev[slot], 0));
             rc = fgfa_depth_plan_feed(W.plan, W.steps, lo, hi, d_depth, d_uniq, W.compute);
