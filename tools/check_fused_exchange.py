@@ -40,7 +40,7 @@ def main():
         import oracle_lib as O
         full_steps, s, e = synth.make_graph(cfg)
         rc, od, ou = O.depth_with_uniq(full_steps, s, e, cfg.n_segs)
-        ok = ok and rc == 0 and bool((od == fd).all() and (ou == fu).all())
+        ok = ok and rc == 0 and bool((od == fd).all() and (ou == fu).all()) and bool((od == rd).all() and (ou == ru).all())
 
     def timed(fn, reps=20):
         for _ in range(3):
@@ -61,6 +61,7 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"config": cfg.name, "n_gpus": world, "parity_fused_vs_nccl_vs_oracle": bool(flag.item()),
+                          "engine_nccl_form": ref.plan.engine, "engine_fused_form": fused.plan.engine,
                           "nccl_step_ms": t_ref, "fused_step_ms": t_fused,
                           "nccl_steps_per_s": cfg.n_steps / (t_ref * 1e-3), "fused_steps_per_s": cfg.n_steps / (t_fused * 1e-3)}))
     dist.destroy_process_group()
