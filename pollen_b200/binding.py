@@ -511,6 +511,13 @@ class MultiDepth:
         self.span_start, self.span_end = _u32(span_start), _u32(span_end)
         self.n_segs, self.n_steps = int(n_segs), int(n_steps)
         self.devices = np.ascontiguousarray(devices, np.int32)
+        if exchange == "nccl" and self.devices.size > 1:
+            # the library dlopens libnccl.so.2 on first use; in a process that will also import torch,
+            # torch's bundled NCCL (same SONAME, newer) must be the one that gets loaded
+            try:
+                import torch  # noqa: F401
+            except ImportError:
+                pass
         h = C.c_void_p()
         rc = lib().fgfa_depth_multi_create(C.byref(h), self.devices.ctypes.data, int(self.devices.size),
                                            self.span_start.ctypes.data, self.span_end.ctypes.data,

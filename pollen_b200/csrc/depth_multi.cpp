@@ -13,9 +13,11 @@
 // No CPU compute path: without CUDA every entry point returns FGFA_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -38,8 +40,15 @@ struct Nccl {
     const char* (*GetErrorString)(int) = nullptr;
     bool load(std::string* why) {
         if (so) return true;
-        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-            so = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        // NCCL writes its NCCL_DEBUG output (even the version banner) to stdout unless told otherwise;
+        // stdout belongs to the caller (`fgfa depth -d` prints the table there)
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+        // FGFA_NCCL_LIB names the library explicitly.  A process that also hosts PyTorch must let torch
+        // load ITS bundled libnccl.so.2 first (same SONAME, newer symbols): the Python binding imports
+        // torch before it creates an NCCL handle for that reason.
+        const char* forced = std::getenv("FGFA_NCCL_LIB");
+        for (const char* name : {forced ? forced : "libnccl.so.2", "libnccl.so.2", "libnccl.so"}) {
+            so = dlopen(name, RTLD_NOW | RTLD_LOCAL);
             if (so) break;
         }
         if (!so) { *why = std::string("libnccl not found: ") + dlerror(); return false; }
@@ -251,7 +260,14 @@ int fgfa_depth_multi_create(fgfa_depth_multi_t** out, const int* devices, int n_
             }
     } else if (n_devices > 1) {
         std::vector<void*> comms((size_t)n_devices, nullptr);
+        // NCCL prints its version banner on STDOUT at the first communicator creation (whatever
+        // NCCL_DEBUG_FILE says); stdout belongs to the caller -- `fgfa depth -d` prints the table there --
+        // so it is pointed at stderr for the duration of the call
+        std::fflush(stdout);
+        const int saved_stdout = dup(1);
+        if (saved_stdout >= 0) dup2(2, 1);
         const int nrc = g_nccl.CommInitAll(comms.data(), n_devices, devices);
+        if (saved_stdout >= 0) { std::fflush(stdout); dup2(saved_stdout, 1); close(saved_stdout); }
         if (nrc != 0)
             return bail(fail(FGFA_ERR_CUDA, std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error")));
         for (int i = 0; i < n_devices; ++i) m->shards[i].nccl_comm = comms[i];
