@@ -43,5 +43,44 @@ res = {
  "full_ms": timed(lambda: f.run(d_steps, st)),
  "nccl_barrier_ms": timed(lambda: dist.barrier()),
 }
+
+# ---- NVLink byte counters around a loop of kernel X alone (NVML field values, KiB, all links summed) ----
+def nvlink_counters():
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        out = []
+        for i in range(world):
+            h = pynvml.nvmlDeviceGetHandleByIndex(i)
+            vals = pynvml.nvmlDeviceGetFieldValues(h, [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX])
+            out.append([int(v.value.ullVal) if v.nvmlReturn == 0 else None for v in vals])
+        return out
+    except Exception as exc:   # noqa: BLE001
+        return f"unavailable: {type(exc).__name__}: {exc}"[:200]
+
+def counted(fn, reps=200):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(dev); dist.barrier()
+    before = nvlink_counters() if rank == 0 else None
+    dist.barrier()
+    for _ in range(reps): fn()
+    torch.cuda.synchronize(dev); dist.barrier()
+    after = nvlink_counters() if rank == 0 else None
+    dist.barrier()
+    if rank != 0 or isinstance(before, str) or isinstance(after, str):
+        return before if isinstance(before, str) else after if isinstance(after, str) else None
+    per_gpu = []
+    for b, a in zip(before, after):
+        per_gpu.append({"tx_bytes_per_launch": None if None in (a[0], b[0]) else (a[0] - b[0]) * 1024 / reps,
+                        "rx_bytes_per_launch": None if None in (a[1], b[1]) else (a[1] - b[1]) * 1024 / reps})
+    return per_gpu
+
+def x_with_barriers():
+    f.hdl.barrier(channel=0); x_only(); f.hdl.barrier(channel=1)
+res["nvlink_kernel_x"] = counted(x_with_barriers)
+res["nvlink_full_step"] = counted(lambda: f.run(d_steps, st))
+n, w = cfg.n_segs, world
+res["model_bytes_per_rank"] = {"partial_depth_in": (w - 1) * (n // w) * 4, "bitmap_rows_in": (cfg.n_paths - len(parts[rank])) * (n // w) // 8,
+                               "result_in": (w - 1) * (n // w) * 5, "result_out_multicast": (n // w) * 5}
 if rank == 0: print(json.dumps({"n_gpus": world, "multicast": bool(f.mc_ptr), **res}))
 dist.destroy_process_group()
