@@ -248,8 +248,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")     # a barrier that does not spin on the GPUs
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     # ---- this rank's shard of the graph ------------------------------------------------
@@ -495,8 +497,6 @@ def main():
         ok = rc == 0 and bool((g_depth == od).all()) and bool((g_uniq == ou).all())
         parity = {"vs_oracle": ok, "n_gpus": world, "engine": engine_name,
                   "checked": f"depth and depth.uniq of all {cfg.n_segs} segments against the C oracle over the whole graph"}
-        if world > 1:
-            del f_steps
     flag = torch.tensor([0 if (parity is None or parity["vs_oracle"]) else 1], dtype=torch.int32, device=dev)
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
@@ -504,6 +504,37 @@ def main():
         if rank == 0:
             print(json.dumps({"metric": METRIC, "error": "PARITY MISMATCH against the oracle", "parity": parity}))
         raise SystemExit(3)
+
+    # ---- end to end through the C ABI at N > 1: ONE process (rank 0) drives all N devices with
+    # fgfa_depth_multi_run_host (host steps in, u64 tables out), the form a compiled `fgfa --gpus N`
+    # uses; the other ranks wait on a CPU barrier so that no NCCL kernel spins on their GPUs
+    if world > 1:
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                hp = torch.from_numpy(f_steps.view(np.int32)).pin_memory()
+                md = pb.MultiDepth(list(range(world)), f_start, f_end, cfg.n_segs, cfg.n_steps, exchange="nccl")
+                d64 = np.empty(cfg.n_segs, np.uint64)
+                u64 = np.empty(cfg.n_segs, np.uint64)
+                md.run_host_ptr(hp.data_ptr(), d64.ctypes.data, u64.ctypes.data)
+                same = bool((d64 == od).all()) and bool((u64 == ou).all())
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    md.run_host_ptr(hp.data_ptr(), d64.ctypes.data, u64.ctypes.data)
+                dt = (time.perf_counter() - t0) / e2e_steps
+                md.close()
+                del hp
+                e2e["per_rank_processes"] = {k: e2e[k] for k in ("value", "ms_per_step", "api", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+                e2e.update({"value": cfg.n_steps / dt, "ms_per_step": dt * 1e3, "steps": e2e_steps, "parity_vs_oracle": same,
+                            "api": f"fgfa_depth_multi_run_host (C ABI, one process driving {world} GPUs, NCCL all-reduce, pinned host steps)",
+                            "h2d_bytes_per_step": 4 * cfg.n_steps, "d2h_bytes_per_step": 5 * cfg.n_segs})
+                if not same:
+                    parity["vs_oracle"] = False
+            except Exception as exc:   # noqa: BLE001 -- keep the per-rank number as the headline
+                e2e["c_abi"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+            del f_steps
+        dist.barrier(group=cpu_group)
 
     # ---- the other BASELINE configs, outside the main timed region ----------------------
     extra = None
