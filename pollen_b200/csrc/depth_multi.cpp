@@ -139,6 +139,21 @@ void lpt(const std::vector<uint32_t>& start, const std::vector<uint32_t>& end, i
 
 int set_device(const Shard& s) { CU(cudaSetDevice(s.device)); return FGFA_OK; }
 
+// u32 / u8 device counters -> the u64 (`usize`, depth.rs:17-18) arrays of the ABI, on a few threads
+template <typename T>
+void widen(const T* src, uint64_t* dst, size_t n) {
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (n < (1u << 20) || hw == 1) { for (size_t i = 0; i < n; ++i) dst[i] = src[i]; return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + hw - 1) / hw;
+    for (unsigned t = 0; t < hw; ++t) {
+        const size_t a = t * per, b = std::min(n, a + per);
+        if (a >= b) break;
+        th.emplace_back([=] { for (size_t i = a; i < b; ++i) dst[i] = src[i]; });
+    }
+    for (auto& t : th) t.join();
+}
+
 }  // namespace
 
 extern "C" {
@@ -408,10 +423,10 @@ int fgfa_depth_multi_download(fgfa_depth_multi_t* m, uint64_t* depth_out, uint64
     }
     CU(cudaStreamSynchronize(s.stream));
     CU(cudaSetDevice(prev));
-    for (uint32_t i = 0; i < n; ++i) depth_out[i] = h[i];            // usize counters at the ABI (depth.rs:17-18)
+    widen(h, depth_out, n);
     if (uniq_out) {
-        if (u8) { const uint8_t* b = reinterpret_cast<const uint8_t*>(h + n); for (uint32_t i = 0; i < n; ++i) uniq_out[i] = b[i]; }
-        else for (uint32_t i = 0; i < n; ++i) uniq_out[i] = h[n + i];
+        if (u8) widen(reinterpret_cast<const uint8_t*>(h + n), uniq_out, n);
+        else widen(h + n, uniq_out, n);
     }
     return FGFA_OK;
 }
