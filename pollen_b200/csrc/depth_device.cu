@@ -53,8 +53,11 @@ constexpr size_t kDefaultBitmapBudget = 64ull << 20;  // stays resident in the 1
 constexpr int kBlocksPerSM = 5;
 constexpr int kGridPerSM = 10;
 constexpr int kPopMinBlocks = 4;       // kernel B register cap (measured, see profiles/)
-// kernel W: 8 rows of 32 steps per sub-chunk, 2 sub-chunks of loads in flight per warp (measured, profiles/r2_*)
+// kernel W: 8 rows of 32 steps per sub-chunk, double-buffered in registers with the loads of the next sub-chunk issued
+// before the ATOMS burst of the current one (the OVL form, window_kernels.cuh; measured, profiles/r2_*)
 constexpr int kWinRows = 8, kWinStages = 2;
+template <bool WITH_SEEN>
+constexpr auto kWindowKernel = fgfa::k_window_count<kWinRows, kWinStages, WITH_SEEN, false, 0, false, true>;
 // the window engine pays a pre-pass (3 launches) and a per-CTA window set-up: below this many
 // steps the stream engine is faster (config B, 20 M steps: 0.05 ms against 0.09 ms)
 constexpr uint64_t kWindowMinSteps = 64ull << 20;
@@ -173,6 +176,8 @@ int launch_window(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     B.n_keys = B.n_bins * B.n_batches;
     B.n_blocks = (n_sub + fgfa::kBinBlock - 1) / fgfa::kBinBlock;
     B.max_span = 2 * fgfa::kWinHalo;
+    B.stable = 0;
+    B.col_mult = 1;
     B.keyrank = pl->d_keyrank;
     B.hist = pl->d_hist;
     B.key_total = pl->d_key_total;
@@ -196,6 +201,7 @@ int launch_window(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     W.n_segs = pl->n_segs;
     W.plane_pitch = pl->plane_pitch;
     W.unit = 1;
+    W.zero = 0;
     W.depth = d_depth;
     W.masks = with_seen ? pl->d_masks + (size_t)batch_lo * pl->plane_pitch : nullptr;
     W.err = pl->d_err;
@@ -203,9 +209,9 @@ int launch_window(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     const uint32_t grid = std::min<uint32_t>((uint32_t)pl->sms, std::max(1u, (n_sub + 31) / 32));
     if (pl->probe_before) CU(cudaEventRecord(pl->probe_before, st));
     if (with_seen)
-        fgfa::k_window_count<kWinRows, kWinStages, true><<<grid, fgfa::kWinThreads, fgfa::window_smem_bytes(true), st>>>(W);
+        kWindowKernel<true><<<grid, fgfa::kWinThreads, fgfa::window_smem_bytes(true), st>>>(W);
     else
-        fgfa::k_window_count<kWinRows, kWinStages, false><<<grid, fgfa::kWinThreads, fgfa::window_smem_bytes(false), st>>>(W);
+        kWindowKernel<false><<<grid, fgfa::kWinThreads, fgfa::window_smem_bytes(false), st>>>(W);
     CU(cudaGetLastError());
     if (pl->probe_after) CU(cudaEventRecord(pl->probe_after, st));
     pl->probe_before = pl->probe_after = nullptr;
@@ -431,8 +437,8 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
             CUB_(cudaMalloc(&pl->d_ticket, 8));
             CUB_(cudaMemset(pl->d_ticket, 0, 8));
             pl->scratch_bytes += (size_t)(subs + n_paths + 1) * 20 + (size_t)keys * pl->max_blocks * 4;
-            cudaFuncSetAttribute(fgfa::k_window_count<kWinRows, kWinStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::window_smem_bytes(true));
-            cudaFuncSetAttribute(fgfa::k_window_count<kWinRows, kWinStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::window_smem_bytes(false));
+            cudaFuncSetAttribute(kWindowKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::window_smem_bytes(true));
+            cudaFuncSetAttribute(kWindowKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgfa::window_smem_bytes(false));
             cudaFuncSetAttribute(fgfa::k_bin_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fgfa::kMaxKeys * 4));
         }
     }

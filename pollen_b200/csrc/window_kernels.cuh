@@ -73,6 +73,8 @@ struct BinParams {
     uint32_t n_keys;                           // n_bins * n_batches; key n_keys is the scattered key
     uint32_t n_blocks;                         // CTAs of S1/S3
     uint32_t max_span;                         // |h1 - h0| above this -> scattered
+    uint32_t stable;                           // 1: entries of a key stay in pool (address) order
+    uint32_t col_mult;                         // histogram column of block b = b * col_mult % n_blocks (coprime; 1 = pool order)
     uint32_t* __restrict__ keyrank;            // [n_sub] key << kRankBits | rank
     uint32_t* __restrict__ hist;               // [(n_keys + 1) * n_blocks], key-major
     uint32_t* __restrict__ key_total;          // [n_keys + 1]
@@ -144,12 +146,23 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_rank(BinParams P) {
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
         const uint32_t before = __popc(peers & ((1u << lane) - 1u));
         uint32_t base = 0;
-        if (d < d_hi && before == 0u) base = atomicAdd(&s_cnt[key], __popc(peers));
+        if (P.stable) {                            // warps take turns: entries of a key keep their pool order
+            for (uint32_t wv = 0; wv < kBinThreads / 32; ++wv) {
+                if ((tid >> 5) == wv && d < d_hi && before == 0u) {
+                    base = s_cnt[key];
+                    s_cnt[key] = base + __popc(peers);
+                }
+                __syncthreads();
+            }
+        } else if (d < d_hi && before == 0u) {
+            base = atomicAdd(&s_cnt[key], __popc(peers));
+        }
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(peers) - 1);
         if (d < d_hi) P.keyrank[d - d_lo] = (key << kRankBits) | (base + before);
     }
     __syncthreads();
-    for (uint32_t i = tid; i <= P.n_keys; i += kBinThreads) P.hist[(size_t)i * P.n_blocks + blockIdx.x] = s_cnt[i];
+    const uint32_t col = (uint32_t)((uint64_t)blockIdx.x * P.col_mult % P.n_blocks);
+    for (uint32_t i = tid; i <= P.n_keys; i += kBinThreads) P.hist[(size_t)i * P.n_blocks + col] = s_cnt[i];
 }
 
 // Engine probe: `samples` evenly spaced sub-chunks; ticket[0] += sampled, ticket[1] += those S1 would
@@ -247,13 +260,14 @@ __global__ void __launch_bounds__(kScanThreads) k_bin_rowscan(BinParams P) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(BinParams P) {
     const uint32_t d_lo = __ldg(P.sub_prefix + P.path_lo), d_hi = __ldg(P.sub_prefix + P.path_hi);
+    const uint32_t col = (uint32_t)((uint64_t)blockIdx.x * P.col_mult % P.n_blocks);
 #pragma unroll
     for (uint32_t round = 0; round < kBinRounds; ++round) {
         const uint32_t d = d_lo + blockIdx.x * kBinBlock + round * kBinThreads + threadIdx.x;
         if (d >= d_hi) continue;
         const uint32_t kr = P.keyrank[d - d_lo];
         const uint32_t key = kr >> kRankBits, rank = kr & ((1u << kRankBits) - 1u);
-        const uint32_t pos = P.key_begin[key] + P.hist[(size_t)key * P.n_blocks + blockIdx.x] + rank;
+        const uint32_t pos = P.key_begin[key] + P.hist[(size_t)key * P.n_blocks + col] + rank;
         P.entries[pos] = P.entry_tmp[d - d_lo];
     }
 }
@@ -272,20 +286,44 @@ struct WindowParams {
     uint32_t n_segs;
     uint64_t plane_pitch;                      // u32 words between two mask planes
     uint32_t unit;                             // must be 1 (see kernel W)
+    uint32_t zero;                             // must be 0: an operand ptxas cannot fold (orders the loads, see kernel W)
     uint32_t* __restrict__ depth;              // [n_segs], zero on entry (or holding earlier batches)
     uint32_t* __restrict__ masks;              // [n_batches][plane_pitch] path-mask planes (WITH_SEEN), zero on entry
     uint32_t* __restrict__ err;
     unsigned long long* __restrict__ stats;    // optional: [0] steps counted in shared memory, [1] steps sent to L2
+    // BITROWS form: one seen-bitmap row per path in global memory (the stream engine's layout, depth_kernels.cuh)
+    uint32_t* __restrict__ bitmap;             // [paths of this pass][words_per_row], row 0 = path row_path_lo
+    uint32_t words_per_row;
+    uint32_t row_path_lo;
 };
 
 constexpr size_t window_smem_bytes(bool with_seen) {
     return with_seen ? (size_t)(kWinSegsSeen + 32) * 8 : (size_t)(kWinSegsDepth + 32) * 4;
 }
 
-// DBG (measurement only, wrong results): 2 = no mask ORs, 3 = neither counters nor masks (loads + address math only).
-template <int ROWS, int STAGES, bool WITH_SEEN, bool STATS = false, int DBG = 0>
+// DBG (measurement only, wrong results): 2 = no mask ORs, 3 = neither counters nor masks (loads + address math only),
+// 4 = a byte store instead of the mask OR (what a byte-map design would pay per step).
+//
+// BITROWS (with WITH_SEEN = false: the window holds counters only, twice as many segments, and there are no path
+// batches): the seen-bits go to one global bitmap row per path instead of shared-memory path masks.  The 32 lanes
+// of a row hold 32 consecutive steps; a maximal run of lanes whose segments are consecutive (s, s+1, ...) covers a
+// contiguous bit range, so the run's first lane alone ORs the whole range -- one ballot, no cross-lane
+// reduction: run length = distance to the next head lane, mask = t ^ (t - 1) with t = heads above this lane.
+// ~7 lanes of 32 issue a RED.OR on config C, to ~1.5 sectors per row; the L2 reduction path is otherwise idle
+// while the shared-memory pipe counts.  Kernel B (k_uniq_popcount) then sums the rows (depth.rs:32).
+//
+// OVL (needs STAGES == 2): the software pipeline ptxas can actually keep.  ptxas tracks every step load of every
+// stage on ONE scoreboard (tools/sass_ctrl.py on the STAGES = 2..4 builds), and a scoreboard is a counter: the
+// first use of one stage's registers waits for ALL outstanding loads, including the ones issued a moment ago for
+// the other stage.  "process, then refill" therefore exposes the full DRAM latency in every iteration, whatever
+// STAGES says.  OVL orders an iteration as: wait for the current buffer -> issue the loads of the next entry ->
+// count the current buffer, so that a warp's loads fly under its own ATOMS burst.  The order is forced with a
+// data dependency ptxas cannot remove: the next entry's address is offset by (OR of the current words) & P.zero.
+template <int ROWS, int STAGES, bool WITH_SEEN, bool STATS = false, int DBG = 0, bool BITROWS = false, bool OVL = false>
 __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P) {
     static_assert(STAGES >= 1 && STAGES <= 4, "stages");
+    static_assert(!OVL || STAGES == 2, "the overlapped pipeline is a double buffer");
+    static_assert(!(BITROWS && WITH_SEEN), "bit rows replace the shared-memory path masks");
     constexpr uint32_t kSegs = win_segs(WITH_SEEN), kBin = win_bin(WITH_SEEN);
     constexpr uint32_t kPitch = kSegs + 32;            // slot kSegs = dummy for steps outside the window
     extern __shared__ uint4 smem_w[];
@@ -293,6 +331,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
     uint32_t* const s_msk = s_cnt + kPitch;                           // [kPitch] (WITH_SEEN)
     constexpr uint32_t kSub = 32u * ROWS;
     constexpr uint32_t NW = kWinThreads / 32;
+    constexpr bool kDescAhead = DBG >= 10;             // experiment: fetch entry descriptors one iteration early
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t pol = make_evict_first_policy();
     uint32_t* const depth_ptr = keep_ptr(P.depth);
@@ -313,11 +352,12 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
         uint32_t h[STAGES][ROWS];
         uint32_t e_path[STAGES];
         uint32_t j = begin + warp;                         // this warp's next entry to PROCESS
-        auto issue_steps = [&](const uint32_t idx, uint32_t (&dst)[ROWS], uint32_t& path_out) {
+        uint2 en_q = make_uint2(0u, 0u);                   // descriptor of the entry STAGES ahead, loaded one iteration early
+        auto issue_steps = [&](const uint32_t idx, uint32_t (&dst)[ROWS], uint32_t& path_out, const bool use_q, const uint32_t dep = 0u) {
             if (idx >= end) return;
-            const uint2 en = __ldg(P.entries + idx);
+            const uint2 en = use_q ? en_q : __ldg(P.entries + idx);
             path_out = en.y & ~kEdgeBit;
-            const uint32_t* src = P.steps + en.x + lane;
+            const uint32_t* src = P.steps + en.x + lane + dep;
             if (!(en.y & kEdgeBit)) {
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) dst[r] = ld_stream_u32(src + 32 * r, pol);
@@ -333,8 +373,42 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
                 }
             }
         };
+        // OVL: lane l of the warp holds the descriptor of the warp's (kb + l)-th entry; one coalesced-by-CTA load
+        // per 32 iterations, a shuffle per iteration -- no descriptor load sits between the step loads and their use.
+        uint2 en_batch = make_uint2(0u, 0u);
+        uint32_t kq = 0, kb = 0;                           // this warp's iteration counter; first iteration of en_batch
+        auto load_batch = [&](const uint32_t k0) {
+            const uint64_t idx = (uint64_t)begin + warp + (uint64_t)(k0 + lane) * NW;
+            en_batch = idx < end ? __ldg(P.entries + idx) : make_uint2(0u, 0u);
+            kb = k0;
+        };
+        auto issue_with = [&](const uint32_t idx, const uint2 en, uint32_t (&dst)[ROWS], uint32_t& path_out, const uint32_t dep) {
+            if (idx >= end) return;
+            path_out = en.y & ~kEdgeBit;
+            const uint32_t* src = P.steps + en.x + lane + dep;
+            if (!(en.y & kEdgeBit)) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) issue_steps(j + NW * s, h[s], e_path[s]);
+                for (int r = 0; r < ROWS; ++r) dst[r] = ld_stream_u32(src + 32 * r, pol);
+            } else {
+                const uint32_t s = __ldg(P.span_s + path_out), e = __ldg(P.span_e + path_out);
+                const uint32_t lo = s > en.x ? s - en.x : 0u;
+                const uint32_t hi = min(e - en.x, kSub);
+                const uint32_t span = hi > lo ? hi - lo : 0u;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const uint32_t off = 32u * r + lane;
+                    dst[r] = (off - lo < span) ? ld_stream_u32(src + 32 * r, pol) : kFiller;
+                }
+            }
+        };
+        if (OVL) {                                         // one buffer in flight
+            load_batch(0);
+            issue_with(j, make_uint2(__shfl_sync(0xFFFFFFFFu, en_batch.x, 0), __shfl_sync(0xFFFFFFFFu, en_batch.y, 0)), h[0], e_path[0], 0u);
+        } else {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) issue_steps(j + NW * s, h[s], e_path[s], false);
+            if (kDescAhead && j + NW * STAGES < end) en_q = __ldg(P.entries + j + NW * STAGES);
+        }
         uint32_t phase = 0;
 
         uint32_t i = begin, key = P.n_keys;
@@ -380,8 +454,31 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
                     const uint32_t lc = min(loc, kSegs);               // outside the window -> the dummy slot
                     if (DBG == 3) { if (loc == 0xFFFFFFF0u) *P.err = 2u; continue; }
                     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cnt_addr + 4u * lc), "r"(one) : "memory");
-                    if (WITH_SEEN && DBG != 2)
+                    if (WITH_SEEN && DBG == 4)       // measurement only: a byte store where the shipped kernel ORs a mask
+                        asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(cnt_addr + lc), "r"(one), "n"(kPitch * 4) : "memory");
+                    else if (WITH_SEEN && DBG != 2)
                         asm volatile("red.shared.or.b32 [%0+%2], %1;" ::"r"(cnt_addr + 4u * lc), "r"(bit), "n"(kPitch * 4) : "memory");
+                }
+                if (BITROWS) {
+                    uint32_t* __restrict__ row = P.bitmap + (size_t)(epath - P.row_path_lo) * P.words_per_row;
+                    const uint32_t sentinel = 0x80000000u >> lane;
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) {
+                        const uint32_t s = hh[r] >> 1;
+                        const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, s, 1);
+                        const bool valid = s < P.n_segs;                       // fillers and bad ids start no run and end one
+                        const bool head = (lane == 0) | (s != prev + 1u) | !valid;
+                        const uint32_t hb = __ballot_sync(0xFFFFFFFFu, head);
+                        if (head && valid) {
+                            const uint32_t t = ((hb >> lane) >> 1) | sentinel;  // heads above this lane; the sentinel ends the row
+                            const uint32_t run = t ^ (t - 1u);                  // (1 << run length) - 1
+                            const uint32_t b = s & 31u;
+                            uint32_t* w = row + (s >> 5);
+                            red_or_b32(w, run << b);
+                            const uint32_t hi = __funnelshift_l(run, 0u, b);    // the part of the run in the next word
+                            if (hi) red_or_b32(w + 1, hi);
+                        }
+                    }
                 }
                 if (STATS) {
 #pragma unroll
@@ -403,13 +500,32 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
                     }
                 }
             };
-            while (j < kend) {
+            // OVL: consume the current buffer's words (scoreboard wait), refill the other buffer, then count.
+            auto ovl_step = [&](uint32_t (&hc)[ROWS], const uint32_t pc, uint32_t (&hn)[ROWS], uint32_t& pn) {
+                uint32_t x = hc[0];
+#pragma unroll
+                for (int r = 1; r < ROWS; ++r) x |= hc[r];
+                const uint32_t dep = x & P.zero;
+                if (kq + 1 - kb == 32u) load_batch(kq + 1);                    // warp-uniform, once per 32 iterations
+                const uint32_t sl = kq + 1 - kb + dep;
+                const uint2 en = make_uint2(__shfl_sync(0xFFFFFFFFu, en_batch.x, sl), __shfl_sync(0xFFFFFFFFu, en_batch.y, sl));
+                issue_with(j + NW, en, hn, pn, dep);
+                process(hc, pc);
+            };
+            while (OVL && j < kend) {
+                if (phase == 0) ovl_step(h[0], e_path[0], h[STAGES > 1 ? 1 : 0], e_path[STAGES > 1 ? 1 : 0]);
+                else ovl_step(h[STAGES > 1 ? 1 : 0], e_path[STAGES > 1 ? 1 : 0], h[0], e_path[0]);
+                phase ^= 1u;
+                j += NW;
+                ++kq;
+            }
+            while (!OVL && j < kend) {
                 switch (phase) {
 #define FGFA_STAGE_CASE(S)                                                                                   \
     case S:                                                                                                  \
         if (S < STAGES) {                                                                                    \
             process(h[S < STAGES ? S : 0], e_path[S < STAGES ? S : 0]);                                      \
-            issue_steps(j + NW * STAGES, h[S < STAGES ? S : 0], e_path[S < STAGES ? S : 0]);                 \
+            issue_steps(j + NW * STAGES, h[S < STAGES ? S : 0], e_path[S < STAGES ? S : 0], kDescAhead);     \
         }                                                                                                    \
         break;
                     FGFA_STAGE_CASE(0)
@@ -418,6 +534,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
                     FGFA_STAGE_CASE(3)
 #undef FGFA_STAGE_CASE
                 }
+                if (kDescAhead && j + NW * (STAGES + 1) < end) en_q = __ldg(P.entries + j + NW * (STAGES + 1));
                 phase = phase + 1 == STAGES ? 0 : phase + 1;
                 j += NW;
             }

@@ -93,8 +93,10 @@ int main(int argc, char** argv) {
     }
 
     const char* only = getenv("UBENCH_ONLY");
-    auto run_variant = [&](const char* name, int rows, bool with_seen, auto&& launch_w, uint32_t max_span) {
+    // seen_kind: 0 = depth only, 1 = shared-memory path masks + kernel B2, 2 = global bitmap rows + kernel B
+    auto run_variant = [&](const char* name, int rows, int seen_kind, auto&& launch_w, uint32_t max_span) {
         if (only && !strstr(name, only)) return;
+        const bool with_seen = seen_kind == 1;
         const uint32_t sub_shift = rows == 8 ? 8 : rows == 16 ? 9 : rows == 4 ? 7 : 10;
         const uint32_t sub = 1u << sub_shift;
         std::vector<uint32_t> prefix(cfg.n_paths + 1, 0);
@@ -113,6 +115,14 @@ int main(int argc, char** argv) {
         B.n_keys = B.n_bins * B.n_batches;
         B.n_blocks = (n_sub + kBinBlock - 1) / kBinBlock;
         B.max_span = max_span;
+        B.stable = getenv("UBENCH_STABLE") ? 1 : 0;
+        B.col_mult = 1;
+        if (getenv("UBENCH_PERMUTE") && B.n_blocks > 2) {      // spread the blocks (= paths) inside every key
+            auto gcd = [](uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; };
+            uint32_t m = (uint32_t)(B.n_blocks * 0.6180339887) | 1u;
+            while (gcd(m, B.n_blocks) != 1) m += 2;
+            B.col_mult = m;
+        }
         if (B.n_keys + 1 > kMaxKeys) { printf("%s: too many keys (%u)\n", name, B.n_keys); return; }
         uint32_t* d_prefix;
         CK(cudaMalloc(&d_prefix, (cfg.n_paths + 1) * 4));
@@ -136,7 +146,11 @@ int main(int argc, char** argv) {
         WindowParams W{};
         W.steps = d_steps; W.entries = d_entries; W.key_begin = d_key_begin; W.span_s = d_ss; W.span_e = d_se;
         W.n_keys = B.n_keys; W.n_batches = B.n_batches; W.path_lo = 0; W.n_segs = cfg.n_segs; W.plane_pitch = pitch;
-        W.depth = d_depth; W.masks = with_seen ? d_masks : nullptr; W.err = d_err; W.stats = d_stats; W.unit = 1;
+        W.depth = d_depth; W.masks = with_seen ? d_masks : nullptr; W.err = d_err; W.stats = d_stats; W.unit = 1; W.zero = 0;
+        W.bitmap = d_bitmap; W.words_per_row = wpr; W.row_path_lo = 0;
+        PopcountParams PQ{};
+        PQ.bitmap = d_bitmap; PQ.n_rows = cfg.n_paths; PQ.words_per_row = wpr; PQ.n_words = n_words; PQ.n_segs = cfg.n_segs;
+        PQ.uniq = d_uniq; PQ.depth = nullptr; PQ.accumulate = 0; PQ.uniq_bytes = 4;
         MaskCountParams Q{};
         Q.masks = d_masks; Q.n_planes = B.n_batches; Q.plane_pitch = pitch; Q.n_segs = cfg.n_segs; Q.uniq = d_uniq;
         Q.accumulate = 0; Q.uniq_bytes = 4;
@@ -158,6 +172,7 @@ int main(int argc, char** argv) {
             if (n_sub) launch_w(grid_w, W);
             CK(cudaEventRecord(ev[3]));
             if (with_seen) k_uniq_from_masks<<<qgrid, 256>>>(Q);
+            if (seen_kind == 2) k_uniq_popcount<4><<<(n_words + kPopThreads - 1) / kPopThreads, kPopThreads>>>(PQ);
             CK(cudaEventRecord(ev[4]));
             CK(cudaEventSynchronize(ev[4]));
             CK(cudaGetLastError());
@@ -187,7 +202,7 @@ int main(int argc, char** argv) {
             CK(cudaMemcpy(g_depth.data(), d_depth, (size_t)cfg.n_segs * 4, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(g_uniq.data(), d_uniq, (size_t)cfg.n_segs * 4, cudaMemcpyDeviceToHost));
             uint64_t bad_d = 0, bad_u = 0;
-            for (uint32_t i = 0; i < cfg.n_segs; ++i) { bad_d += g_depth[i] != o_depth[i]; bad_u += with_seen && g_uniq[i] != o_uniq[i]; }
+            for (uint32_t i = 0; i < cfg.n_segs; ++i) { bad_d += g_depth[i] != o_depth[i]; bad_u += seen_kind != 0 && g_uniq[i] != o_uniq[i]; }
             printf("  mismatches depth=%llu uniq=%llu %s\n", (unsigned long long)bad_d, (unsigned long long)bad_u,
                    (bad_d | bad_u) ? "FAIL" : "PARITY OK");
         }
@@ -199,8 +214,20 @@ int main(int argc, char** argv) {
 #define VARIANT(NAME, ROWS, STAGES, SEEN, STATS, DBG, SPAN)                                                   \
     do {                                                                                                      \
         SETUP((k_window_count<ROWS, STAGES, SEEN, STATS, DBG>), window_smem_bytes(SEEN));                     \
-        run_variant(NAME, ROWS, SEEN, [&](uint32_t g, WindowParams& W) {                                      \
+        run_variant(NAME, ROWS, SEEN ? 1 : 0, [&](uint32_t g, WindowParams& W) {                              \
             k_window_count<ROWS, STAGES, SEEN, STATS, DBG><<<g, kWinThreads, window_smem_bytes(SEEN)>>>(W); }, SPAN); \
+    } while (0)
+#define VARIANT_OVL(NAME, ROWS, SEEN, DBG, SPAN)                                                              \
+    do {                                                                                                      \
+        SETUP((k_window_count<ROWS, 2, SEEN, false, DBG, false, true>), window_smem_bytes(SEEN));             \
+        run_variant(NAME, ROWS, SEEN ? 1 : 0, [&](uint32_t g, WindowParams& W) {                              \
+            k_window_count<ROWS, 2, SEEN, false, DBG, false, true><<<g, kWinThreads, window_smem_bytes(SEEN)>>>(W); }, SPAN); \
+    } while (0)
+#define VARIANT_ROWS(NAME, ROWS, STAGES, DBG, SPAN)                                                           \
+    do {                                                                                                      \
+        SETUP((k_window_count<ROWS, STAGES, false, false, DBG, true>), window_smem_bytes(false));             \
+        run_variant(NAME, ROWS, 2, [&](uint32_t g, WindowParams& W) {                                         \
+            k_window_count<ROWS, STAGES, false, false, DBG, true><<<g, kWinThreads, window_smem_bytes(false)>>>(W); }, SPAN); \
     } while (0)
     const uint32_t ms_def = 2 * kWinHalo;
     {   // where the steps go (statistics build, not timed meaningfully)
@@ -211,6 +238,12 @@ int main(int argc, char** argv) {
         if (st[0] + st[1]) printf("  rows=8: in-window %.3f%%  to-L2 %.3f%% of steps\n", 100.0 * st[0] / (double)(st[0] + st[1]), 100.0 * st[1] / (double)(st[0] + st[1]));
     }
     VARIANT("W r8 s2", 8, 2, true, false, 0, ms_def);
+    VARIANT_OVL("OVL W r8", 8, true, 0, ms_def);
+    VARIANT_OVL("OVL depth-only r8", 8, false, 0, ms_def);
+    VARIANT_OVL("OVL DBG3 loads only", 8, true, 3, ms_def);
+    VARIANT_OVL("OVL DBG2 no mask ORs", 8, true, 2, ms_def);
+    VARIANT_ROWS("BITROWS r8 s2", 8, 2, 0, ms_def);
+    VARIANT_ROWS("BITROWS r8 s3", 8, 3, 0, ms_def);
     VARIANT("W r8 s3", 8, 3, true, false, 0, ms_def);
     VARIANT("W r8 s4", 8, 4, true, false, 0, ms_def);
     VARIANT("W r16 s2", 16, 2, true, false, 0, ms_def);
@@ -221,5 +254,9 @@ int main(int argc, char** argv) {
     // measurement-only variants (results are wrong by construction)
     VARIANT("DBG2 no mask ORs", 8, 3, true, false, 2, ms_def);
     VARIANT("DBG3 loads only", 8, 3, true, false, 3, ms_def);
+    VARIANT("DBG4 byte store for OR s2", 8, 2, true, false, 4, ms_def);
+    VARIANT("DESC-AHEAD W r8 s2", 8, 2, true, false, 10, ms_def);
+    VARIANT("DESC-AHEAD W r8 s3", 8, 3, true, false, 10, ms_def);
+    VARIANT("DBG2 no mask ORs s2", 8, 2, true, false, 2, ms_def);
     return 0;
 }
