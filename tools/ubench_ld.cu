@@ -199,6 +199,87 @@ __global__ void __launch_bounds__(1024, 1) k3_ring(const uint32_t* __restrict__ 
     }
 }
 
+// K4: every warp runs its own ring of D 1 KiB slots: lane 0 issues a cp.async.bulk for the entry D iterations ahead
+// into the slot it has just drained (no producer warp, no empty barriers: the consumer is the producer).
+template <int D, bool FENCE>
+__global__ void __launch_bounds__(1024, 1) k4_self_tma(const uint32_t* __restrict__ steps, const uint2* __restrict__ entries,
+                                                       uint32_t n_entries, uint32_t* out) {
+    extern __shared__ __align__(1024) uint8_t smem_r[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_r) + warp * D * 1024;
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem_r) + 32 * D * 1024 + warp * D * 8;
+    const uint32_t per = (n_entries + gridDim.x - 1) / gridDim.x;
+    const uint32_t begin = min(n_entries, blockIdx.x * per), end = min(n_entries, begin + per);
+    const uint64_t pol = make_evict_first_policy();
+    if (lane < D) mbar_init(bars + 8 * lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    auto issue = [&](uint32_t idx, uint32_t slot) {
+        if (idx < end && lane == 0) {
+            const uint2 en = __ldg(entries + idx);
+            if (FENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bars + 8 * slot, 1024);
+            bulk_g2s(ring + slot * 1024, steps + en.x, 1024, bars + 8 * slot, pol);
+        }
+    };
+    uint32_t j = begin + warp;
+#pragma unroll
+    for (int d = 0; d < D; ++d) issue(j + 32 * d, d);
+    uint32_t acc = 0, k = 0;
+    for (; j < end; j += 32, ++k) {
+        const uint32_t slot = k % D;
+        mbar_wait(bars + 8 * slot, (k / D) & 1);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(smem_r + (warp * D + slot) * 1024) + lane;
+        uint32_t h[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) h[r] = src[32 * r];
+        __syncwarp();
+        issue(j + 32 * D, slot);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc ^= h[r];
+    }
+    if (acc == 0x9E3779B9u) *out = acc;
+}
+
+// K5: the same ring filled with per-lane 16-byte cp.async (LDGSTS), one commit group per entry, wait_group D-1.
+template <int D>
+__global__ void __launch_bounds__(1024, 1) k5_self_cpasync(const uint32_t* __restrict__ steps, const uint2* __restrict__ entries,
+                                                           uint32_t n_entries, uint32_t* out) {
+    extern __shared__ __align__(1024) uint8_t smem_r[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_r) + warp * D * 1024;
+    const uint32_t per = (n_entries + gridDim.x - 1) / gridDim.x;
+    const uint32_t begin = min(n_entries, blockIdx.x * per), end = min(n_entries, begin + per);
+    auto issue = [&](uint32_t idx, uint32_t slot) {
+        if (idx < end) {
+            const uint2 en = __ldg(entries + idx);
+            const uint32_t* src = steps + en.x + 4 * lane;
+            const uint32_t dst = ring + slot * 1024 + 16 * lane;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(src + 128) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t j = begin + warp;
+#pragma unroll
+    for (int d = 0; d < D; ++d) issue(j + 32 * d, d);
+    uint32_t acc = 0, k = 0;
+    for (; j < end; j += 32, ++k) {
+        const uint32_t slot = k % D;
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+        __syncwarp();
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(smem_r + (warp * D + slot) * 1024) + lane;
+        uint32_t h[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) h[r] = src[32 * r];
+        __syncwarp();
+        issue(j + 32 * D, slot);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc ^= h[r];
+    }
+    if (acc == 0x9E3779B9u) *out = acc;
+}
+
 struct Cfg { const char* name; uint32_t n_segs, n_paths; uint64_t n_steps; int kind; uint32_t jitter; };
 
 int main(int argc, char** argv) {
@@ -315,6 +396,18 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(k3_ring<SPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big));          \
         timeit("K3 TMA ring slots/warp=" #SPW, [&] { k3_ring<SPW><<<sms, 1024, big>>>(d_steps, d_entries, n_sub, d_out); }); \
     } while (0)
-    K3(1); K3(2); K3(3); K3(4); K3(6);
+    K3(2); K3(4);
+#define K4(D, F)                                                                                                \
+    do {                                                                                                        \
+        CK(cudaFuncSetAttribute(k4_self_tma<D, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big));     \
+        timeit("K4 self-service TMA ring D=" #D " fence=" #F, [&] { k4_self_tma<D, F><<<sms, 1024, big>>>(d_steps, d_entries, n_sub, d_out); }); \
+    } while (0)
+    K4(1, false); K4(2, false); K4(3, false); K4(4, false); K4(2, true); K4(3, true);
+#define K5(D)                                                                                                   \
+    do {                                                                                                        \
+        CK(cudaFuncSetAttribute(k5_self_cpasync<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big));    \
+        timeit("K5 self-service cp.async ring D=" #D, [&] { k5_self_cpasync<D><<<sms, 1024, big>>>(d_steps, d_entries, n_sub, d_out); }); \
+    } while (0)
+    K5(1); K5(2); K5(3); K5(4);
     return 0;
 }

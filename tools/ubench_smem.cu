@@ -9,10 +9,12 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
-constexpr int kWords = 40960;   // 160 KiB of u32 counters
+constexpr int kWords = 40960;   // 160 KiB of u32 counters (the pair ops use the first 20480 as counters, the rest as masks)
 constexpr int kBytes = 40960;   // + 40 KiB of seen bytes
 
-enum Op { kAtomAdd, kStoreU8, kAtomAddStoreU8, kLoad32, kStore32, kAtomOrBitmap, kAtomAddU16, kAtomAddRet, kStoreU8Cond };
+enum Op { kAtomAdd, kStoreU8, kAtomAddStoreU8, kLoad32, kStore32, kAtomOrBitmap, kAtomAddU16, kAtomAddRet, kStoreU8Cond,
+          kAtomAddReg, kAtomOrReg, kAtomOrHeads7, kAtomOrHeads7Distinct, kAtomOrHeads3,
+          kAtomAddOpaque, kAtomOrRet, kAtomAddOrPair, kAtomAddOrPairRet };
 
 // lane offsets: pattern 0 = consecutive segments, 1 = stride ~2.46 (config C walk), 2 = random in window
 __device__ __forceinline__ uint32_t lane_off(int pattern, uint32_t lane, uint32_t it) {
@@ -33,11 +35,13 @@ __global__ void __launch_bounds__(1024, 1) k_smem(int pattern, int iters, unsign
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t base = warp * 997u;
     uint32_t acc = 0;
+    const uint32_t opaque_one = *sink | 1u;       // *sink is 0
     const long long t0 = clock64();
 #pragma unroll 4
     for (int it = 0; it < iters; ++it) {
         uint32_t loc = base + lane_off(pattern, lane, it);
         if (loc >= 40000u) loc -= 40000u;
+        if ((OP == kAtomAddOrPair || OP == kAtomAddOrPairRet) && loc >= 20000u) loc -= 20000u;
         if (OP == kAtomAdd || OP == kAtomAddStoreU8) {
             const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + loc);
             asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
@@ -50,6 +54,45 @@ __global__ void __launch_bounds__(1024, 1) k_smem(int pattern, int iters, unsign
         if (OP == kAtomOrBitmap) {
             const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + (loc >> 5));
             asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(1u << (loc & 31)) : "memory");
+        }
+        if (OP == kAtomAddReg) {                      // what kernel W issues: register operand (ATOMS.ADD, not POPC.INC)
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + loc);
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"((uint32_t)iters >> 30 | 1u) : "memory");
+        }
+        if (OP == kAtomOrReg) {
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + loc);
+            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(1u << (it & 31)) : "memory");
+        }
+        if (OP == kAtomOrHeads7 || OP == kAtomOrHeads7Distinct || OP == kAtomOrHeads3) {
+            // run heads of a row: few active lanes; same-word lanes (bit rows) or distinct words
+            const bool head = OP == kAtomOrHeads3 ? (lane % 11u == 0u) : (lane % 5u == 0u);
+            if (head) {
+                const uint32_t w = OP == kAtomOrHeads7Distinct ? loc : (loc >> 5);
+                const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + w);
+                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(0x1Fu << (loc & 31)) : "memory");
+            }
+        }
+        if (OP == kAtomAddOpaque) {                   // ATOMS.ADD RZ, [a], R: operand ptxas cannot fold
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + loc);
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(opaque_one) : "memory");
+        }
+        if (OP == kAtomOrRet) {
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + loc);
+            uint32_t old;
+            asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(1u << (it & 31)) : "memory");
+            acc += old;
+        }
+        if (OP == kAtomAddOrPair) {                   // kernel W's pair: counter word + mask word
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + loc);
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(opaque_one) : "memory");
+            asm volatile("red.shared.or.b32 [%0+81920], %1;" ::"r"(a), "r"(1u << (it & 31)) : "memory");
+        }
+        if (OP == kAtomAddOrPairRet) {
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + loc);
+            uint32_t o1, o2;
+            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o1) : "r"(a), "r"(opaque_one) : "memory");
+            asm volatile("atom.shared.or.b32 %0, [%1+81920], %2;" : "=r"(o2) : "r"(a), "r"(1u << (it & 31)) : "memory");
+            acc += o1 + o2;
         }
         if (OP == kAtomAddU16) {
             const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + (loc >> 1));
@@ -91,6 +134,7 @@ int main() {
     uint32_t* d_sink;
     CK(cudaMalloc(&d_out, 256 * 8));
     CK(cudaMalloc(&d_sink, 4));
+    CK(cudaMemset(d_sink, 0, 4));
     run<kLoad32>("LDS.32", sms, d_out, d_sink);
     run<kStore32>("STS.32", sms, d_out, d_sink);
     run<kStoreU8>("STS.U8", sms, d_out, d_sink);
@@ -100,5 +144,14 @@ int main() {
     run<kAtomAddStoreU8>("red.add.u32 + STS.U8", sms, d_out, d_sink);
     run<kAtomOrBitmap>("red.shared.or bitmap", sms, d_out, d_sink);
     run<kAtomAddU16>("red.add packed u16", sms, d_out, d_sink);
+    run<kAtomAddReg>("red.add.u32 reg operand", sms, d_out, d_sink);
+    run<kAtomOrReg>("red.or.b32 32 lanes", sms, d_out, d_sink);
+    run<kAtomOrHeads7>("red.or 7 head lanes, bit rows", sms, d_out, d_sink);
+    run<kAtomOrHeads7Distinct>("red.or 7 lanes, distinct words", sms, d_out, d_sink);
+    run<kAtomOrHeads3>("red.or 3 head lanes, bit rows", sms, d_out, d_sink);
+    run<kAtomAddOpaque>("ATOMS.ADD RZ (reg operand)", sms, d_out, d_sink);
+    run<kAtomOrRet>("ATOMS.OR with return", sms, d_out, d_sink);
+    run<kAtomAddOrPair>("ATOMS.ADD RZ + ATOMS.OR RZ", sms, d_out, d_sink);
+    run<kAtomAddOrPairRet>("ATOMS.ADD ret + ATOMS.OR ret", sms, d_out, d_sink);
     return 0;
 }

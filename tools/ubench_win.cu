@@ -94,7 +94,7 @@ int main(int argc, char** argv) {
 
     const char* only = getenv("UBENCH_ONLY");
     // seen_kind: 0 = depth only, 1 = shared-memory path masks + kernel B2, 2 = global bitmap rows + kernel B
-    auto run_variant = [&](const char* name, int rows, int seen_kind, auto&& launch_w, uint32_t max_span) {
+    auto run_variant = [&](const char* name, int rows, int seen_kind, auto&& launch_w, uint32_t max_span, uint32_t bin_override = 0) {
         if (only && !strstr(name, only)) return;
         const bool with_seen = seen_kind == 1;
         const uint32_t sub_shift = rows == 8 ? 8 : rows == 16 ? 9 : rows == 4 ? 7 : 10;
@@ -109,7 +109,7 @@ int main(int argc, char** argv) {
         BinParams B{};
         B.steps = d_steps; B.span_s = d_ss; B.span_e = d_se; B.path_lo = 0; B.path_hi = cfg.n_paths; B.mask_path_lo = 0;
         B.sub_shift = sub_shift; B.n_segs = cfg.n_segs;
-        B.bin_segs = win_bin(with_seen);
+        B.bin_segs = bin_override ? bin_override : win_bin(with_seen);
         B.n_bins = (cfg.n_segs + B.bin_segs - 1) / B.bin_segs;
         B.n_batches = with_seen ? (cfg.n_paths + 31) / 32 : 1;
         B.n_keys = B.n_bins * B.n_batches;
@@ -223,6 +223,12 @@ int main(int argc, char** argv) {
         run_variant(NAME, ROWS, SEEN ? 1 : 0, [&](uint32_t g, WindowParams& W) {                              \
             k_window_count<ROWS, 2, SEEN, false, DBG, false, true><<<g, kWinThreads, window_smem_bytes(SEEN)>>>(W); }, SPAN); \
     } while (0)
+#define VARIANT_RING(NAME, D, SEEN, DBG, SPAN)                                                                \
+    do {                                                                                                      \
+        SETUP((k_window_ring<D, SEEN, false, DBG>), ring_smem_bytes<D>(SEEN));                                \
+        run_variant(NAME, 8, SEEN ? 1 : 0, [&](uint32_t g, WindowParams& W) {                                 \
+            k_window_ring<D, SEEN, false, DBG><<<g, kWinThreads, ring_smem_bytes<D>(SEEN)>>>(W); }, SPAN, ring_win_bin<D>(SEEN)); \
+    } while (0)
 #define VARIANT_ROWS(NAME, ROWS, STAGES, DBG, SPAN)                                                           \
     do {                                                                                                      \
         SETUP((k_window_count<ROWS, STAGES, false, false, DBG, true>), window_smem_bytes(false));             \
@@ -242,6 +248,14 @@ int main(int argc, char** argv) {
     VARIANT_OVL("OVL depth-only r8", 8, false, 0, ms_def);
     VARIANT_OVL("OVL DBG3 loads only", 8, true, 3, ms_def);
     VARIANT_OVL("OVL DBG2 no mask ORs", 8, true, 2, ms_def);
+    VARIANT_RING("RING D=1 W", 1, true, 0, ms_def);
+    VARIANT_RING("RING D=2 W", 2, true, 0, ms_def);
+    VARIANT_RING("RING D=1 depth-only", 1, false, 0, ms_def);
+    VARIANT_RING("RING D=2 depth-only", 2, false, 0, ms_def);
+    VARIANT_RING("RING D=1 DBG3 loads only", 1, true, 3, ms_def);
+    VARIANT_RING("RING D=2 DBG3 loads only", 2, true, 3, ms_def);
+    VARIANT_RING("RING D=1 DBG2 no mask ORs", 1, true, 2, ms_def);
+    VARIANT_RING("RING D=2 DBG2 no mask ORs", 2, true, 2, ms_def);
     VARIANT_ROWS("BITROWS r8 s2", 8, 2, 0, ms_def);
     VARIANT_ROWS("BITROWS r8 s3", 8, 3, 0, ms_def);
     VARIANT("W r8 s3", 8, 3, true, false, 0, ms_def);
