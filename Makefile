@@ -56,8 +56,10 @@ build/depth_example: examples/depth.c include/flatgfa.h $(LIBDIR)/libflatgfa.so
 oracle:
 	$(MAKE) -C oracle
 
-tools: build/ubench build/sort_dedup_probe build/ubench_win build/ubench_smem
-build/ubench_win: tools/ubench_win.cu $(CSRC)/window_kernels.cuh $(CSRC)/depth_kernels.cuh build/ubench
+tools: build/ubench build/sort_dedup_probe build/ubench_win build/ubench_smem build/ubench_ld
+build/ubench_ld: tools/ubench_ld.cu $(CSRC)/window_kernels.cuh $(CSRC)/depth_kernels.cuh build/ubench
+	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench_ld.cu build/synth.o -o $@
+build/ubench_win: tools/ubench_win.cu tools/experimental_window.cuh $(CSRC)/window_kernels.cuh $(CSRC)/depth_kernels.cuh build/ubench
 	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench_win.cu build/depth_oracle.o build/synth.o -o $@
 build/ubench_smem: tools/ubench_smem.cu
 	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 tools/ubench_smem.cu -o $@

@@ -57,7 +57,7 @@ constexpr int kPopMinBlocks = 4;       // kernel B register cap (measured, see p
 // before the ATOMS burst of the current one (the OVL form, window_kernels.cuh; measured, profiles/r2_*)
 constexpr int kWinRows = 8, kWinStages = 2;
 template <bool WITH_SEEN>
-constexpr auto kWindowKernel = fgfa::k_window_count<kWinRows, kWinStages, WITH_SEEN, false, 0, false, true>;
+constexpr auto kWindowKernel = fgfa::k_window_count<kWinRows, kWinStages, WITH_SEEN, false, 0, true>;
 // the window engine pays a pre-pass (3 launches) and a per-CTA window set-up: below this many
 // steps the stream engine is faster (config B, 20 M steps: 0.05 ms against 0.09 ms)
 constexpr uint64_t kWindowMinSteps = 64ull << 20;
@@ -176,8 +176,6 @@ int launch_window(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     B.n_keys = B.n_bins * B.n_batches;
     B.n_blocks = (n_sub + fgfa::kBinBlock - 1) / fgfa::kBinBlock;
     B.max_span = 2 * fgfa::kWinHalo;
-    B.stable = 0;
-    B.col_mult = 1;
     B.keyrank = pl->d_keyrank;
     B.hist = pl->d_hist;
     B.key_total = pl->d_key_total;

@@ -73,8 +73,6 @@ struct BinParams {
     uint32_t n_keys;                           // n_bins * n_batches; key n_keys is the scattered key
     uint32_t n_blocks;                         // CTAs of S1/S3
     uint32_t max_span;                         // |h1 - h0| above this -> scattered
-    uint32_t stable;                           // 1: entries of a key stay in pool (address) order
-    uint32_t col_mult;                         // histogram column of block b = b * col_mult % n_blocks (coprime; 1 = pool order)
     uint32_t* __restrict__ keyrank;            // [n_sub] key << kRankBits | rank
     uint32_t* __restrict__ hist;               // [(n_keys + 1) * n_blocks], key-major
     uint32_t* __restrict__ key_total;          // [n_keys + 1]
@@ -146,23 +144,12 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_rank(BinParams P) {
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
         const uint32_t before = __popc(peers & ((1u << lane) - 1u));
         uint32_t base = 0;
-        if (P.stable) {                            // warps take turns: entries of a key keep their pool order
-            for (uint32_t wv = 0; wv < kBinThreads / 32; ++wv) {
-                if ((tid >> 5) == wv && d < d_hi && before == 0u) {
-                    base = s_cnt[key];
-                    s_cnt[key] = base + __popc(peers);
-                }
-                __syncthreads();
-            }
-        } else if (d < d_hi && before == 0u) {
-            base = atomicAdd(&s_cnt[key], __popc(peers));
-        }
+        if (d < d_hi && before == 0u) base = atomicAdd(&s_cnt[key], __popc(peers));
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(peers) - 1);
         if (d < d_hi) P.keyrank[d - d_lo] = (key << kRankBits) | (base + before);
     }
     __syncthreads();
-    const uint32_t col = (uint32_t)((uint64_t)blockIdx.x * P.col_mult % P.n_blocks);
-    for (uint32_t i = tid; i <= P.n_keys; i += kBinThreads) P.hist[(size_t)i * P.n_blocks + col] = s_cnt[i];
+    for (uint32_t i = tid; i <= P.n_keys; i += kBinThreads) P.hist[(size_t)i * P.n_blocks + blockIdx.x] = s_cnt[i];
 }
 
 // Engine probe: `samples` evenly spaced sub-chunks; ticket[0] += sampled, ticket[1] += those S1 would
@@ -260,14 +247,13 @@ __global__ void __launch_bounds__(kScanThreads) k_bin_rowscan(BinParams P) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(BinParams P) {
     const uint32_t d_lo = __ldg(P.sub_prefix + P.path_lo), d_hi = __ldg(P.sub_prefix + P.path_hi);
-    const uint32_t col = (uint32_t)((uint64_t)blockIdx.x * P.col_mult % P.n_blocks);
 #pragma unroll
     for (uint32_t round = 0; round < kBinRounds; ++round) {
         const uint32_t d = d_lo + blockIdx.x * kBinBlock + round * kBinThreads + threadIdx.x;
         if (d >= d_hi) continue;
         const uint32_t kr = P.keyrank[d - d_lo];
         const uint32_t key = kr >> kRankBits, rank = kr & ((1u << kRankBits) - 1u);
-        const uint32_t pos = P.key_begin[key] + P.hist[(size_t)key * P.n_blocks + col] + rank;
+        const uint32_t pos = P.key_begin[key] + P.hist[(size_t)key * P.n_blocks + blockIdx.x] + rank;
         P.entries[pos] = P.entry_tmp[d - d_lo];
     }
 }
@@ -291,10 +277,6 @@ struct WindowParams {
     uint32_t* __restrict__ masks;              // [n_batches][plane_pitch] path-mask planes (WITH_SEEN), zero on entry
     uint32_t* __restrict__ err;
     unsigned long long* __restrict__ stats;    // optional: [0] steps counted in shared memory, [1] steps sent to L2
-    // BITROWS form: one seen-bitmap row per path in global memory (the stream engine's layout, depth_kernels.cuh)
-    uint32_t* __restrict__ bitmap;             // [paths of this pass][words_per_row], row 0 = path row_path_lo
-    uint32_t words_per_row;
-    uint32_t row_path_lo;
 };
 
 constexpr size_t window_smem_bytes(bool with_seen) {
@@ -304,14 +286,6 @@ constexpr size_t window_smem_bytes(bool with_seen) {
 // DBG (measurement only, wrong results): 2 = no mask ORs, 3 = neither counters nor masks (loads + address math only),
 // 4 = a byte store instead of the mask OR (what a byte-map design would pay per step).
 //
-// BITROWS (with WITH_SEEN = false: the window holds counters only, twice as many segments, and there are no path
-// batches): the seen-bits go to one global bitmap row per path instead of shared-memory path masks.  The 32 lanes
-// of a row hold 32 consecutive steps; a maximal run of lanes whose segments are consecutive (s, s+1, ...) covers a
-// contiguous bit range, so the run's first lane alone ORs the whole range -- one ballot, no cross-lane
-// reduction: run length = distance to the next head lane, mask = t ^ (t - 1) with t = heads above this lane.
-// ~7 lanes of 32 issue a RED.OR on config C, to ~1.5 sectors per row; the L2 reduction path is otherwise idle
-// while the shared-memory pipe counts.  Kernel B (k_uniq_popcount) then sums the rows (depth.rs:32).
-//
 // OVL (needs STAGES == 2): the software pipeline ptxas can actually keep.  ptxas tracks every step load of every
 // stage on ONE scoreboard (tools/sass_ctrl.py on the STAGES = 2..4 builds), and a scoreboard is a counter: the
 // first use of one stage's registers waits for ALL outstanding loads, including the ones issued a moment ago for
@@ -319,11 +293,10 @@ constexpr size_t window_smem_bytes(bool with_seen) {
 // STAGES says.  OVL orders an iteration as: wait for the current buffer -> issue the loads of the next entry ->
 // count the current buffer, so that a warp's loads fly under its own ATOMS burst.  The order is forced with a
 // data dependency ptxas cannot remove: the next entry's address is offset by (OR of the current words) & P.zero.
-template <int ROWS, int STAGES, bool WITH_SEEN, bool STATS = false, int DBG = 0, bool BITROWS = false, bool OVL = false>
+template <int ROWS, int STAGES, bool WITH_SEEN, bool STATS = false, int DBG = 0, bool OVL = false>
 __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P) {
     static_assert(STAGES >= 1 && STAGES <= 4, "stages");
     static_assert(!OVL || STAGES == 2, "the overlapped pipeline is a double buffer");
-    static_assert(!(BITROWS && WITH_SEEN), "bit rows replace the shared-memory path masks");
     constexpr uint32_t kSegs = win_segs(WITH_SEEN), kBin = win_bin(WITH_SEEN);
     constexpr uint32_t kPitch = kSegs + 32;            // slot kSegs = dummy for steps outside the window
     extern __shared__ uint4 smem_w[];
@@ -331,7 +304,6 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
     uint32_t* const s_msk = s_cnt + kPitch;                           // [kPitch] (WITH_SEEN)
     constexpr uint32_t kSub = 32u * ROWS;
     constexpr uint32_t NW = kWinThreads / 32;
-    constexpr bool kDescAhead = DBG >= 10;             // experiment: fetch entry descriptors one iteration early
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t pol = make_evict_first_policy();
     uint32_t* const depth_ptr = keep_ptr(P.depth);
@@ -352,12 +324,11 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
         uint32_t h[STAGES][ROWS];
         uint32_t e_path[STAGES];
         uint32_t j = begin + warp;                         // this warp's next entry to PROCESS
-        uint2 en_q = make_uint2(0u, 0u);                   // descriptor of the entry STAGES ahead, loaded one iteration early
-        auto issue_steps = [&](const uint32_t idx, uint32_t (&dst)[ROWS], uint32_t& path_out, const bool use_q, const uint32_t dep = 0u) {
+        auto issue_steps = [&](const uint32_t idx, uint32_t (&dst)[ROWS], uint32_t& path_out) {
             if (idx >= end) return;
-            const uint2 en = use_q ? en_q : __ldg(P.entries + idx);
+            const uint2 en = __ldg(P.entries + idx);
             path_out = en.y & ~kEdgeBit;
-            const uint32_t* src = P.steps + en.x + lane + dep;
+            const uint32_t* src = P.steps + en.x + lane;
             if (!(en.y & kEdgeBit)) {
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) dst[r] = ld_stream_u32(src + 32 * r, pol);
@@ -406,8 +377,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
             issue_with(j, make_uint2(__shfl_sync(0xFFFFFFFFu, en_batch.x, 0), __shfl_sync(0xFFFFFFFFu, en_batch.y, 0)), h[0], e_path[0], 0u);
         } else {
 #pragma unroll
-            for (int s = 0; s < STAGES; ++s) issue_steps(j + NW * s, h[s], e_path[s], false);
-            if (kDescAhead && j + NW * STAGES < end) en_q = __ldg(P.entries + j + NW * STAGES);
+            for (int s = 0; s < STAGES; ++s) issue_steps(j + NW * s, h[s], e_path[s]);
         }
         uint32_t phase = 0;
 
@@ -459,27 +429,6 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
                     else if (WITH_SEEN && DBG != 2)
                         asm volatile("red.shared.or.b32 [%0+%2], %1;" ::"r"(cnt_addr + 4u * lc), "r"(bit), "n"(kPitch * 4) : "memory");
                 }
-                if (BITROWS) {
-                    uint32_t* __restrict__ row = P.bitmap + (size_t)(epath - P.row_path_lo) * P.words_per_row;
-                    const uint32_t sentinel = 0x80000000u >> lane;
-#pragma unroll
-                    for (int r = 0; r < ROWS; ++r) {
-                        const uint32_t s = hh[r] >> 1;
-                        const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, s, 1);
-                        const bool valid = s < P.n_segs;                       // fillers and bad ids start no run and end one
-                        const bool head = (lane == 0) | (s != prev + 1u) | !valid;
-                        const uint32_t hb = __ballot_sync(0xFFFFFFFFu, head);
-                        if (head && valid) {
-                            const uint32_t t = ((hb >> lane) >> 1) | sentinel;  // heads above this lane; the sentinel ends the row
-                            const uint32_t run = t ^ (t - 1u);                  // (1 << run length) - 1
-                            const uint32_t b = s & 31u;
-                            uint32_t* w = row + (s >> 5);
-                            red_or_b32(w, run << b);
-                            const uint32_t hi = __funnelshift_l(run, 0u, b);    // the part of the run in the next word
-                            if (hi) red_or_b32(w + 1, hi);
-                        }
-                    }
-                }
                 if (STATS) {
 #pragma unroll
                     for (int r = 0; r < ROWS; ++r) { const uint32_t seg = hh[r] >> 1; if (seg - w_lo < w_n) ++n_in; else if (seg < P.n_segs) ++n_out; }
@@ -525,7 +474,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
     case S:                                                                                                  \
         if (S < STAGES) {                                                                                    \
             process(h[S < STAGES ? S : 0], e_path[S < STAGES ? S : 0]);                                      \
-            issue_steps(j + NW * STAGES, h[S < STAGES ? S : 0], e_path[S < STAGES ? S : 0], kDescAhead);     \
+            issue_steps(j + NW * STAGES, h[S < STAGES ? S : 0], e_path[S < STAGES ? S : 0]);                 \
         }                                                                                                    \
         break;
                     FGFA_STAGE_CASE(0)
@@ -534,7 +483,6 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
                     FGFA_STAGE_CASE(3)
 #undef FGFA_STAGE_CASE
                 }
-                if (kDescAhead && j + NW * (STAGES + 1) < end) en_q = __ldg(P.entries + j + NW * (STAGES + 1));
                 phase = phase + 1 == STAGES ? 0 : phase + 1;
                 j += NW;
             }
@@ -559,254 +507,6 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
     };
 
     // equal shares of the binned entries and of the scattered entries for every CTA
-    {
-        const uint32_t per = (n_binned + gridDim.x - 1) / gridDim.x;
-        const uint32_t b0 = min(n_binned, blockIdx.x * per);
-        run_range(b0, min(n_binned, b0 + per), false);
-    }
-    {
-        const uint32_t n_sc = n_entries - n_binned;
-        const uint32_t per = (n_sc + gridDim.x - 1) / gridDim.x;
-        const uint32_t s0 = n_binned + min(n_sc, blockIdx.x * per);
-        run_range(s0, min(n_entries, s0 + per), true);
-    }
-    if (STATS) {
-        atomicAdd(P.stats, n_in);
-        atomicAdd(P.stats + 1, n_out);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// kernel W, ring form (k_window_ring): the same counting, but the sub-chunks arrive through a per-warp ring of D
-// 1 KiB shared-memory slots filled by TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx).
-//
-// Why: the register pipeline of k_window_count cannot run more than one sub-chunk ahead -- ptxas tracks the step
-// loads of every stage on one scoreboard (tools/sass_ctrl.py), so a warp has at most 1 KiB in flight and the SM
-// 32 KiB, against the ~64 KiB the HBM latency needs (tools/ubench_ld.cu: 0.33 ms for the register form, 0.27 /
-// 0.245 ms for this ring with D = 1 / 2 on config C's 1.6 GB, loads only).  A bulk copy is tracked by its mbarrier,
-// not by a scoreboard, costs one instruction of one lane per KiB, and lands in shared memory without passing
-// through the LSU pipe the ATOMS are queued in.  Each warp is its own producer: as soon as it has read a slot
-// into registers (8 conflict-free LDS) it issues the copy for the entry D iterations ahead into that slot and
-// only then counts -- no producer warp, no "empty" barriers.  More than 64 bulk copies in flight per SM collapse
-// the TMA throughput (D = 3: 0.455 ms), so D is 1 or 2.  The ring takes 32*D KiB from the window:
-//   D = 1: 24576 segments with path masks (bin 12288), 49152 without (bin 36864)
-//   D = 2: 20480 / 40960                   (bin  8192 / 28672)
-// Sub-chunks on a span boundary are not copied (their 1 KiB may leave the pool): the consumer loads them with
-// predicated LDGs as k_window_count does; their slot's barrier is completed by a plain arrive so that the
-// parity of every slot keeps advancing once per use.
-// ---------------------------------------------------------------------------
-constexpr uint32_t kSmemMax = 232448;               // 227 KiB of dynamic shared memory per CTA on sm_100
-template <int D> __host__ __device__ constexpr uint32_t ring_bytes() { return 32u * D * 1024u + 32u * D * 16u; }   // slots + {mbarrier, descriptor}
-template <int D> __host__ __device__ constexpr uint32_t ring_win_segs(bool with_seen) {
-    return ((kSmemMax - ring_bytes<D>()) / (with_seen ? 8u : 4u) - 32u) / 1024u * 1024u;
-}
-template <int D> __host__ __device__ constexpr uint32_t ring_win_bin(bool with_seen) { return ring_win_segs<D>(with_seen) - 2 * kWinHalo; }
-template <int D> constexpr size_t ring_smem_bytes(bool with_seen) {
-    return ring_bytes<D>() + (size_t)(ring_win_segs<D>(with_seen) + 32) * (with_seen ? 8 : 4);
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t a) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "W_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@!p bra W_%=;\n"
-        "}\n" ::"r"(a), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint64_t pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
-}
-
-template <int D, bool WITH_SEEN, bool STATS = false, int DBG = 0>
-__global__ void __launch_bounds__(kWinThreads, 1) k_window_ring(WindowParams P) {
-    static_assert(D == 1 || D == 2, "more than 64 bulk copies in flight per SM collapse the TMA throughput");
-    constexpr int ROWS = 8;
-    constexpr uint32_t kSegs = ring_win_segs<D>(WITH_SEEN), kBin = ring_win_bin<D>(WITH_SEEN);
-    constexpr uint32_t kPitch = kSegs + 32;            // slot kSegs = dummy for steps outside the window
-    constexpr uint32_t kSub = 32u * ROWS;
-    constexpr uint32_t NW = kWinThreads / 32;
-    extern __shared__ uint4 smem_w[];
-    // [ring 32 x D x 1 KiB][meta 32 x D x {mbarrier u64, descriptor uint2}][counters kPitch][masks kPitch]
-    uint8_t* const s_base = reinterpret_cast<uint8_t*>(smem_w);
-    uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(s_base + ring_bytes<D>());
-    uint32_t* const s_msk = s_cnt + kPitch;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_base) + warp * D * 1024u;
-    const uint32_t meta = (uint32_t)__cvta_generic_to_shared(s_base) + 32u * D * 1024u + warp * D * 16u;   // +0 mbarrier, +8 descriptor
-    const uint2* const s_desc = reinterpret_cast<const uint2*>(s_base + 32u * D * 1024u + warp * D * 16u + 8u);
-    const uint64_t pol = make_evict_first_policy();
-    uint32_t* const depth_ptr = keep_ptr(P.depth);
-    const uint32_t cnt_addr = (uint32_t)__cvta_generic_to_shared(s_cnt);
-    const uint32_t one = P.unit;                       // see k_window_count
-    unsigned long long n_in = 0, n_out = 0;
-
-    for (uint32_t i = tid; i < (WITH_SEEN ? 2 * kPitch : kPitch); i += kWinThreads) s_cnt[i] = 0u;
-    if (lane < D) mbar_init(meta + 16u * lane, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-
-    const uint32_t n_binned = __ldg(P.key_begin + P.n_keys), n_entries = __ldg(P.key_begin + P.n_keys + 1);
-    uint32_t kt = 0;                                       // slot uses of this warp so far: slot = kt % D, parity = (kt / D) & 1
-
-    auto run_range = [&](const uint32_t begin, const uint32_t end, const bool scattered) {
-        if (begin >= end) return;                          // block-uniform
-        uint32_t j = begin + warp;                         // this warp's next entry to PROCESS
-        // lane l holds the descriptor of the warp's (kb + l)-th entry of this range: one load per 32 issues
-        uint2 en_batch = make_uint2(0u, 0u);
-        uint32_t ki = 0, kb = 0;                           // issues so far in this range; first issue index of en_batch
-        auto load_batch = [&](const uint32_t k0) {
-            const uint64_t idx = (uint64_t)begin + warp + (uint64_t)(k0 + lane) * NW;
-            en_batch = idx < end ? __ldg(P.entries + idx) : make_uint2(0u, 0u);
-            kb = k0;
-        };
-        // issue the copy of this warp's ki-th entry of the range into `slot` (warp-uniform)
-        auto issue = [&](const uint32_t slot) {
-            const uint64_t idx = (uint64_t)begin + warp + (uint64_t)ki * NW;
-            if (idx < end) {
-                if (ki - kb == 32u) load_batch(ki);
-                const uint32_t ex = __shfl_sync(0xFFFFFFFFu, en_batch.x, ki - kb), ey = __shfl_sync(0xFFFFFFFFu, en_batch.y, ki - kb);
-                if (lane == 0) {
-                    const uint32_t bar = meta + 16u * slot;
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(bar + 8u), "r"(ex), "r"(ey) : "memory");
-                    if (!(ey & kEdgeBit)) {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot was read through the generic proxy
-                        mbar_expect_tx(bar, kSub * 4u);
-                        bulk_g2s(ring + slot * 1024u, P.steps + ex, kSub * 4u, bar, pol);
-                    } else {
-                        mbar_arrive(bar);                  // nothing to copy: complete the phase
-                    }
-                }
-            }
-            ++ki;
-        };
-        load_batch(0);
-#pragma unroll
-        for (int d = 0; d < D; ++d) issue((kt + d) % D);
-        __syncwarp();
-
-        uint32_t i = begin, key = P.n_keys;
-        if (!scattered) {                                  // key of the first entry
-            uint32_t lo = 0, hi = P.n_keys;
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (__ldg(P.key_begin + mid) <= i) lo = mid; else hi = mid;
-            }
-            key = lo;
-        }
-        uint32_t cur_bin = 0xFFFFFFFFu;                    // window whose counters are in shared memory
-        uint32_t w_lo = 0, w_n = 0;
-        auto flush_counters = [&]() {                      // counters -> depth[]; leaves them zero
-            for (uint32_t k = tid; k < w_n; k += kWinThreads) {
-                const uint32_t v = s_cnt[k];
-                if (v) { red_add_u32(depth_ptr + w_lo + k, v); s_cnt[k] = 0u; }
-            }
-        };
-        while (i < end) {
-            const uint32_t kend = scattered ? end : min(end, __ldg(P.key_begin + key + 1));
-            if (i >= kend) { ++key; continue; }
-            const uint32_t bin = scattered ? 0xFFFFFFFEu : key / P.n_batches;
-            const uint32_t batch = scattered ? 0u : key - bin * P.n_batches;
-            if (bin != cur_bin) {                          // block-uniform
-                if (cur_bin < 0xFFFFFFFEu) {
-                    if (!WITH_SEEN) __syncthreads();       // (with uniq the mask flush has already synchronised)
-                    flush_counters();
-                    __syncthreads();
-                }
-                cur_bin = bin;
-                w_lo = scattered ? 0u : (bin * kBin > kWinHalo ? bin * kBin - kWinHalo : 0u);
-                w_n = scattered ? 0u : min(kSegs, P.n_segs - w_lo);    // segments this window really holds
-            }
-            while (j < kend) {
-                // ---- take the sub-chunk out of its slot ----
-                const uint32_t slot = kt % D;
-                uint32_t hh[ROWS];
-                mbar_wait(meta + 16u * slot, (kt / D) & 1u);
-                const uint2 en = s_desc[2 * slot];                      // lane 0 stored it before it armed the barrier
-                const uint32_t epath = en.y & ~kEdgeBit;
-                if (!(en.y & kEdgeBit)) {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(s_base + (warp * D + slot) * 1024u) + lane;
-#pragma unroll
-                    for (int r = 0; r < ROWS; ++r) hh[r] = src[32 * r];
-                } else {
-                    const uint32_t* src = P.steps + en.x + lane;
-                    const uint32_t s = __ldg(P.span_s + epath), e = __ldg(P.span_e + epath);
-                    const uint32_t lo = s > en.x ? s - en.x : 0u;
-                    const uint32_t hi = min(e - en.x, kSub);
-                    const uint32_t span = hi > lo ? hi - lo : 0u;
-#pragma unroll
-                    for (int r = 0; r < ROWS; ++r) {
-                        const uint32_t off = 32u * r + lane;
-                        hh[r] = (off - lo < span) ? ld_stream_u32(src + 32 * r, pol) : kFiller;
-                    }
-                }
-                __syncwarp();                                          // every lane has its words: the slot is free
-                issue(slot);
-                ++kt;
-                // ---- count it (as k_window_count) ----
-                uint32_t mx = 0;
-                const uint32_t bit = bit_of(epath - P.path_lo);        // 1 << ((path - path_lo) % 32)
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const uint32_t seg = hh[r] >> 1, loc = seg - w_lo;
-                    mx = max(mx, loc);
-                    const uint32_t lc = min(loc, kSegs);               // outside the window -> the dummy slot
-                    if (DBG == 3) { if (loc == 0xFFFFFFF0u) *P.err = 2u; continue; }
-                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cnt_addr + 4u * lc), "r"(one) : "memory");
-                    if (WITH_SEEN && DBG != 2)
-                        asm volatile("red.shared.or.b32 [%0+%2], %1;" ::"r"(cnt_addr + 4u * lc), "r"(bit), "n"(kPitch * 4) : "memory");
-                }
-                if (STATS) {
-#pragma unroll
-                    for (int r = 0; r < ROWS; ++r) { const uint32_t seg = hh[r] >> 1; if (seg - w_lo < w_n) ++n_in; else if (seg < P.n_segs) ++n_out; }
-                }
-                if (__any_sync(0xFFFFFFFFu, mx >= w_n)) {              // rare: steps outside the window
-                    const uint32_t rel = epath - P.path_lo;
-                    uint32_t* __restrict__ plane = WITH_SEEN ? P.masks + (size_t)(rel >> 5) * P.plane_pitch : nullptr;
-#pragma unroll
-                    for (int r = 0; r < ROWS; ++r) {
-                        const uint32_t seg = hh[r] >> 1;
-                        if (seg - w_lo < w_n) continue;
-                        if (seg < P.n_segs) {
-                            red_add_u32(depth_ptr + seg, 1u);
-                            if (WITH_SEEN) red_or_b32(plane + seg, bit);
-                        } else if (hh[r] != kFiller) {
-                            *P.err = 1u;
-                        }
-                    }
-                }
-                j += NW;
-            }
-            i = kend;
-            if (WITH_SEEN && !scattered) {
-                // ---- the key is counted: masks -> this batch's plane; leaves them zero ----
-                __syncthreads();
-                uint32_t* __restrict__ plane = P.masks + (size_t)batch * P.plane_pitch + w_lo;
-                for (uint32_t k = tid; k < w_n; k += kWinThreads) {
-                    const uint32_t v = s_msk[k];
-                    if (v) { red_or_b32(plane + k, v); s_msk[k] = 0u; }
-                }
-                __syncthreads();
-            }
-            ++key;
-        }
-        if (cur_bin < 0xFFFFFFFEu) {
-            if (!WITH_SEEN) __syncthreads();
-            flush_counters();
-            __syncthreads();
-        }
-    };
-
     {
         const uint32_t per = (n_binned + gridDim.x - 1) / gridDim.x;
         const uint32_t b0 = min(n_binned, blockIdx.x * per);

@@ -72,3 +72,36 @@ def test_exchange_kernel_uses_multicast(sass):
     for name, ops in _kernels(sass, "k_uniq_exchange").items():
         assert ops["LDGMC"] > 0, name
         assert ops["STG"] > 0 and ops["ATOMG"] == 0, name
+
+
+def test_window_kernel_counts_in_shared_memory_and_overlaps_its_loads():
+    """kernel W (the shipped OVL instantiations): shared-memory ATOMS for counters and path masks, descriptors
+    by shuffle, no spills -- and, in program order, every burst of ATOMS is preceded by the step loads of the
+    NEXT sub-chunk (the order DESIGN.md 4.1 relies on: ptxas tracks all step loads on one scoreboard, so
+    'count, then refill' would expose the DRAM latency in every iteration)."""
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m and cur:
+            funcs[cur].append(m.group(1))
+    ws = {k: v for k, v in funcs.items() if "k_window_count" in k}
+    assert len(ws) == 2, list(ws)                       # with and without path masks
+    for name, ops in ws.items():
+        base = [o.split(".")[0] for o in ops]
+        assert "STL" not in base and "LDL" not in base, name
+        assert base.count("ATOMS") >= 8 and "SHFL" in base and "REDG" in base, name
+        # first ATOMS burst of the main loop: the 8 streaming step loads (LDG.E.NA...) just before it
+        first = base.index("ATOMS")
+        window = ops[max(0, first - 400):first]
+        assert sum(o.startswith("LDG.E.NA") for o in window) >= 8, name
+        # ... and none between the bursts' ATOMS (the refill is not interleaved after the counting starts)
+        last = len(base) - 1 - base[::-1].index("ATOMS")
+        assert base[first:last].count("ATOMS") >= 16, name

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../pollen_b200/csrc/window_kernels.cuh"
+#include "experimental_window.cuh"
 
 extern "C" {
 int fgfa_synth_spans(uint32_t, uint64_t, uint32_t, uint64_t, uint32_t*, uint32_t*);
@@ -93,7 +94,7 @@ int main(int argc, char** argv) {
     }
 
     const char* only = getenv("UBENCH_ONLY");
-    // seen_kind: 0 = depth only, 1 = shared-memory path masks + kernel B2, 2 = global bitmap rows + kernel B
+    // seen_kind: 0 = depth only, 1 = shared-memory path masks + kernel B2
     auto run_variant = [&](const char* name, int rows, int seen_kind, auto&& launch_w, uint32_t max_span, uint32_t bin_override = 0) {
         if (only && !strstr(name, only)) return;
         const bool with_seen = seen_kind == 1;
@@ -115,14 +116,6 @@ int main(int argc, char** argv) {
         B.n_keys = B.n_bins * B.n_batches;
         B.n_blocks = (n_sub + kBinBlock - 1) / kBinBlock;
         B.max_span = max_span;
-        B.stable = getenv("UBENCH_STABLE") ? 1 : 0;
-        B.col_mult = 1;
-        if (getenv("UBENCH_PERMUTE") && B.n_blocks > 2) {      // spread the blocks (= paths) inside every key
-            auto gcd = [](uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; };
-            uint32_t m = (uint32_t)(B.n_blocks * 0.6180339887) | 1u;
-            while (gcd(m, B.n_blocks) != 1) m += 2;
-            B.col_mult = m;
-        }
         if (B.n_keys + 1 > kMaxKeys) { printf("%s: too many keys (%u)\n", name, B.n_keys); return; }
         uint32_t* d_prefix;
         CK(cudaMalloc(&d_prefix, (cfg.n_paths + 1) * 4));
@@ -147,10 +140,6 @@ int main(int argc, char** argv) {
         W.steps = d_steps; W.entries = d_entries; W.key_begin = d_key_begin; W.span_s = d_ss; W.span_e = d_se;
         W.n_keys = B.n_keys; W.n_batches = B.n_batches; W.path_lo = 0; W.n_segs = cfg.n_segs; W.plane_pitch = pitch;
         W.depth = d_depth; W.masks = with_seen ? d_masks : nullptr; W.err = d_err; W.stats = d_stats; W.unit = 1; W.zero = 0;
-        W.bitmap = d_bitmap; W.words_per_row = wpr; W.row_path_lo = 0;
-        PopcountParams PQ{};
-        PQ.bitmap = d_bitmap; PQ.n_rows = cfg.n_paths; PQ.words_per_row = wpr; PQ.n_words = n_words; PQ.n_segs = cfg.n_segs;
-        PQ.uniq = d_uniq; PQ.depth = nullptr; PQ.accumulate = 0; PQ.uniq_bytes = 4;
         MaskCountParams Q{};
         Q.masks = d_masks; Q.n_planes = B.n_batches; Q.plane_pitch = pitch; Q.n_segs = cfg.n_segs; Q.uniq = d_uniq;
         Q.accumulate = 0; Q.uniq_bytes = 4;
@@ -172,7 +161,6 @@ int main(int argc, char** argv) {
             if (n_sub) launch_w(grid_w, W);
             CK(cudaEventRecord(ev[3]));
             if (with_seen) k_uniq_from_masks<<<qgrid, 256>>>(Q);
-            if (seen_kind == 2) k_uniq_popcount<4><<<(n_words + kPopThreads - 1) / kPopThreads, kPopThreads>>>(PQ);
             CK(cudaEventRecord(ev[4]));
             CK(cudaEventSynchronize(ev[4]));
             CK(cudaGetLastError());
@@ -219,21 +207,15 @@ int main(int argc, char** argv) {
     } while (0)
 #define VARIANT_OVL(NAME, ROWS, SEEN, DBG, SPAN)                                                              \
     do {                                                                                                      \
-        SETUP((k_window_count<ROWS, 2, SEEN, false, DBG, false, true>), window_smem_bytes(SEEN));             \
+        SETUP((k_window_count<ROWS, 2, SEEN, false, DBG, true>), window_smem_bytes(SEEN));             \
         run_variant(NAME, ROWS, SEEN ? 1 : 0, [&](uint32_t g, WindowParams& W) {                              \
-            k_window_count<ROWS, 2, SEEN, false, DBG, false, true><<<g, kWinThreads, window_smem_bytes(SEEN)>>>(W); }, SPAN); \
+            k_window_count<ROWS, 2, SEEN, false, DBG, true><<<g, kWinThreads, window_smem_bytes(SEEN)>>>(W); }, SPAN); \
     } while (0)
 #define VARIANT_RING(NAME, D, SEEN, DBG, SPAN)                                                                \
     do {                                                                                                      \
         SETUP((k_window_ring<D, SEEN, false, DBG>), ring_smem_bytes<D>(SEEN));                                \
         run_variant(NAME, 8, SEEN ? 1 : 0, [&](uint32_t g, WindowParams& W) {                                 \
             k_window_ring<D, SEEN, false, DBG><<<g, kWinThreads, ring_smem_bytes<D>(SEEN)>>>(W); }, SPAN, ring_win_bin<D>(SEEN)); \
-    } while (0)
-#define VARIANT_ROWS(NAME, ROWS, STAGES, DBG, SPAN)                                                           \
-    do {                                                                                                      \
-        SETUP((k_window_count<ROWS, STAGES, false, false, DBG, true>), window_smem_bytes(false));             \
-        run_variant(NAME, ROWS, 2, [&](uint32_t g, WindowParams& W) {                                         \
-            k_window_count<ROWS, STAGES, false, false, DBG, true><<<g, kWinThreads, window_smem_bytes(false)>>>(W); }, SPAN); \
     } while (0)
     const uint32_t ms_def = 2 * kWinHalo;
     {   // where the steps go (statistics build, not timed meaningfully)
@@ -256,8 +238,6 @@ int main(int argc, char** argv) {
     VARIANT_RING("RING D=2 DBG3 loads only", 2, true, 3, ms_def);
     VARIANT_RING("RING D=1 DBG2 no mask ORs", 1, true, 2, ms_def);
     VARIANT_RING("RING D=2 DBG2 no mask ORs", 2, true, 2, ms_def);
-    VARIANT_ROWS("BITROWS r8 s2", 8, 2, 0, ms_def);
-    VARIANT_ROWS("BITROWS r8 s3", 8, 3, 0, ms_def);
     VARIANT("W r8 s3", 8, 3, true, false, 0, ms_def);
     VARIANT("W r8 s4", 8, 4, true, false, 0, ms_def);
     VARIANT("W r16 s2", 16, 2, true, false, 0, ms_def);
@@ -269,8 +249,6 @@ int main(int argc, char** argv) {
     VARIANT("DBG2 no mask ORs", 8, 3, true, false, 2, ms_def);
     VARIANT("DBG3 loads only", 8, 3, true, false, 3, ms_def);
     VARIANT("DBG4 byte store for OR s2", 8, 2, true, false, 4, ms_def);
-    VARIANT("DESC-AHEAD W r8 s2", 8, 2, true, false, 10, ms_def);
-    VARIANT("DESC-AHEAD W r8 s3", 8, 3, true, false, 10, ms_def);
     VARIANT("DBG2 no mask ORs s2", 8, 2, true, false, 2, ms_def);
     return 0;
 }
