@@ -90,6 +90,16 @@ __device__ __forceinline__ uint32_t find_sub_path(const uint32_t* __restrict__ p
     return lo;
 }
 
+// One handle of the pool for the pre-pass: read-only path, no L1 allocation, 64-byte L2 prefetch hint (a sample
+// uses 4 bytes of whatever the L2 fetches from DRAM for it).  S1 0.060 -> 0.056 ms on config C; the hint size
+// itself makes no difference, and neither does the CTA count (one wave or two): S1 is bound by one DRAM row
+// activation per sample (profiles/r2_ubench_win_11_prepass.log).
+__device__ __forceinline__ uint32_t ld_sample(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // S1: key + rank inside the block + per-block histogram.
 // ---------------------------------------------------------------------------
@@ -115,7 +125,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_rank(BinParams P) {
             const uint32_t a = (s & ~31u) + ((d - __ldg(P.sub_prefix + p)) << P.sub_shift);
             path[round] = p; span_e[round] = e;
             last_d[round] = __ldg(P.sub_prefix + p + 1) - 1u;       // last sub-chunk of this path
-            s_h0[round * kBinThreads + tid] = __ldg(P.steps + max(a, s)) >> 1;
+            s_h0[round * kBinThreads + tid] = ld_sample(P.steps + max(a, s)) >> 1;
             P.entry_tmp[d - d_lo] = make_uint2(a, p | ((a < s || (uint64_t)a + sub > e) ? kEdgeBit : 0u));
         }
     }
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_rank(BinParams P) {
         if (d < d_hi) {
             const uint32_t p = find_sub_path(P.sub_prefix, P.path_lo, P.path_hi, d);
             const uint32_t s = __ldg(P.span_s + p);
-            v = __ldg(P.steps + max((s & ~31u) + ((d - __ldg(P.sub_prefix + p)) << P.sub_shift), s)) >> 1;
+            v = ld_sample(P.steps + max((s & ~31u) + ((d - __ldg(P.sub_prefix + p)) << P.sub_shift), s)) >> 1;
         }
         s_h0[kBinBlock] = v;
     }
