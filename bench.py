@@ -273,40 +273,68 @@ def main():
         # Preferred exchange: popcount fused with a reduce-scatter/all-gather over NVLink peer
         # memory (kernel X).  It is checked against the NCCL engine once, here, and dropped if
         # symmetric memory is unavailable on this box or the results differ.
-        try:
-            fused = sharding.FusedShardedDepth(ls, le, cfg.n_segs, dev, [len(p) for p in parts])
-            st0 = torch.cuda.current_stream(dev)
-            eng.run(d_steps, st0)
-            fused.run(d_steps, st0)
-            torch.cuda.synchronize(dev)
-            same = torch.equal(eng.depth, fused.depth) and torch.equal(eng.uniq, fused.uniq)
+        # Candidates, each checked against the NCCL engine once, here, and dropped if symmetric memory is
+        # unavailable on this box or the results differ; the fastest by a start-up probe on the real shard runs:
+        #   pull  kernel X: popcount fused with a reduce-scatter / all-gather by peer LOADS + multicast stores
+        #   push  kernels P + R: partial depth and u8 uniq counts travel as peer STORES, owners reduce locally
+        st0 = torch.cuda.current_stream(dev)
 
-            def probe(e, reps=8):
-                for _ in range(3):
-                    e.run(d_steps, st0)
+        def probe(e, reps=8):
+            for _ in range(3):
+                e.run(d_steps, st0)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st0)
+            for _ in range(reps):
+                e.run(d_steps, st0)
+            b.record(st0)
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / reps
+
+        names = {"pull": "fused popcount + reduce-scatter/all-gather over NVLink peer memory (kernel X: peer loads%s)",
+                 "push": "fused popcount + push of the partials into the slice owners + local reduce + all-gather over NVLink peer memory (kernels P + R: peer stores%s)",
+                 "push-window": "window engine per rank, then push of [depth u32 | uniq u8] into the slice owners + local reduce + all-gather over NVLink peer memory (kernels P + R: peer stores%s)"}
+        forms = [f for f in os.environ.get("FGFA_FUSED_FORMS", "pull,push,push-window").split(",") if f in names]
+        if engine_name != "window":
+            forms = [f for f in forms if f != "push-window"]
+        try:
+            eng.run(d_steps, st0)
+            torch.cuda.synchronize(dev)
+            cands, bad_any = {}, 0.0
+            for form in forms:
+                f = sharding.FusedShardedDepth(ls, le, cfg.n_segs, dev, [len(p) for p in parts], form=form.split("-")[0],
+                                               local_engine="window" if form == "push-window" else "stream")
+                f.run(d_steps, st0)
                 torch.cuda.synchronize(dev)
-                dist.barrier()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(st0)
-                for _ in range(reps):
-                    e.run(d_steps, st0)
-                b.record(st0)
-                torch.cuda.synchronize(dev)
-                return a.elapsed_time(b) / reps
-            t = torch.tensor([probe(eng), probe(fused), 0.0 if same else 1.0], dtype=torch.float64, device=dev)
+                same = torch.equal(eng.depth, f.depth) and torch.equal(eng.uniq, f.uniq)
+                cands[form] = (f, same)
+            t = torch.tensor([probe(eng)] + [probe(cands[f][0]) for f in forms] + [0.0 if cands[f][1] else 1.0 for f in forms],
+                             dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_nccl, t_fused, bad = (float(x) for x in t.tolist())
-            if bad == 0.0 and t_fused < t_nccl:        # every rank takes the same decision
-                eng = fused
-                exchange = "fused popcount + reduce-scatter/all-gather over NVLink peer memory (kernel X%s); probe: %.3f ms vs %.3f ms with nccl" % (
-                    ", multicast stores" if fused.mc_ptr else "", t_fused, t_nccl)
+            vals = [float(x) for x in t.tolist()]
+            t_nccl, t_forms, bad = vals[0], vals[1:1 + len(forms)], vals[1 + len(forms):]
+            ok = [(tf, f) for tf, f, bd in zip(t_forms, forms, bad) if bd == 0.0]
+            probe_txt = "; probe: nccl %.3f ms" % t_nccl + "".join(
+                ", %s %.3f ms%s" % (f, tf, "" if bd == 0.0 else " (MISMATCH)") for f, tf, bd in zip(forms, t_forms, bad))
+            if ok and min(ok)[0] < t_nccl:             # every rank takes the same decision
+                best = min(ok)[1]
+                eng = cands[best][0]
+                exchange = names[best] % (", multicast stores" if eng.mc_ptr else "") + probe_txt
             else:
-                exchange += "; probe: %.3f ms vs %.3f ms with the fused exchange%s" % (t_nccl, t_fused, "" if bad == 0.0 else " (MISMATCH)")
-                del fused
+                exchange += probe_txt
+            for f in forms:
+                if cands[f][0] is not eng:
+                    cands[f] = None
         except Exception as exc:  # symmetric memory not available: keep NCCL
-            exchange += f" (fused exchange unavailable: {type(exc).__name__})"
+            exchange += f" (fused exchange unavailable: {type(exc).__name__}: {exc})"[:300]
     stream = torch.cuda.current_stream(dev)
-    launches_per_step = eng.plan.launches(True) if isinstance(eng, sharding.ShardedDepth) else 2   # S1-S3 + W + B2 / A + B, or A + X
+    if isinstance(eng, sharding.ShardedDepth):
+        launches_per_step = eng.plan.launches(True)                    # S1-S3 + W + B2, or A + B
+    elif eng.form == "push":
+        launches_per_step = (eng.plan.launches(True) if eng.local_engine == "window" else 1) + 2    # ... + P + R
+    else:
+        launches_per_step = 2                                          # A + X
     engine_name = eng.plan.engine
 
     def barrier():

@@ -128,6 +128,27 @@ int fgfa_exchange_uniq_depth(int n_ranks, int rank, const void* const* bitmaps, 
                              uint64_t off_partial, uint64_t off_final_depth, uint64_t off_final_uniq,
                              void* cuda_stream);
 
+/* The same exchange as PUSH + local reduce (kernels P and R; faster than the pull form above from 4 GPUs on:
+ * partials travel as posted peer stores, the bitmaps never leave their GPU).  Slices and receive buffers:
+ * fgfa_exchange_recv_bytes(n_ranks, n_segs) bytes per rank, any 256-byte aligned peer-mapped memory.
+ *   fgfa_exchange_push    popcount this rank's `rows` bitmap rows (and clear them), and store the u8 counts
+ *                         and this rank's partial depth, slice by slice, into slot `rank` of the slice owner's
+ *                         receive buffer (recv_bufs[owner]).  With partial_uniq_u8 != NULL (u8 counts that a
+ *                         plan with fgfa_depth_plan_set_uniq_width(1) has already produced, e.g. by the window
+ *                         engine; the buffer must be readable up to a multiple of 32 bytes) the counts are
+ *                         forwarded instead and bitmap / rows are ignored.
+ *   -- inter-rank barrier (caller) --
+ *   fgfa_exchange_reduce  add the n_ranks slots of this rank's slice and store final depth (u32) / uniq (u8)
+ *                         into every rank's result buffers (multicast_base as for fgfa_exchange_uniq_depth).
+ *   -- inter-rank barrier (caller) --
+ * <= 255 paths in the whole graph. */
+size_t fgfa_exchange_recv_bytes(int n_ranks, uint32_t n_segs);
+int fgfa_exchange_push(int n_ranks, int rank, void* bitmap, uint32_t rows, const void* partial_depth,
+                       const void* partial_uniq_u8, void* const* recv_bufs, uint32_t n_segs, void* cuda_stream);
+int fgfa_exchange_reduce(int n_ranks, int rank, const void* recv_buf, void* const* final_depths,
+                         void* const* final_uniqs, uint32_t n_segs, void* multicast_base,
+                         uint64_t off_final_depth, uint64_t off_final_uniq, void* cuda_stream);
+
 /* ---- multi-GPU, one process driving N devices ------------------------------------------
  * The reference's host is one compiled process (flatgfa/src/cli/main.rs:57-188, cmds.rs:234-245), so
  * this is the form a Rust `fgfa --gpus N` binds.  Whole paths are partitioned over the devices by step

@@ -91,6 +91,9 @@ EXPORTS = {
     "fgfa_depth_plan_use_bitmap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fgfa_depth_plan_run_stream_only": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgfa_exchange_uniq_depth": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "fgfa_exchange_recv_bytes": (C.c_size_t, [C.c_int, C.c_uint32]),
+    "fgfa_exchange_push": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "fgfa_exchange_reduce": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "fgfa_depth_plan_set_uniq_width": (C.c_int, [C.c_void_p, C.c_int]),
     "fgfa_depth_multi_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]),
     "fgfa_depth_multi_destroy": (None, [C.c_void_p]),
@@ -493,6 +496,27 @@ def exchange_uniq_depth(n_ranks, rank, bitmaps, rows, partial_depths, final_dept
                                           off_partial, off_final_depth, off_final_uniq, stream or None))
 
 
+def exchange_recv_bytes(n_ranks: int, n_segs: int) -> int:
+    """Bytes of one rank's receive buffer for the push form of the exchange."""
+    return int(lib().fgfa_exchange_recv_bytes(int(n_ranks), int(n_segs)))
+
+
+def exchange_push(n_ranks, rank, bitmap, rows, partial_depth, recv_bufs, n_segs, stream=0, partial_uniq=0):
+    """Kernel P (see fgfa_exchange_push): this rank's u8 uniq counts + partial depth into the slice owners' slots.
+    ``partial_uniq``: device pointer to u8 counts that already exist (then ``bitmap`` / ``rows`` are ignored)."""
+    P = C.c_void_p * n_ranks
+    _check(lib().fgfa_exchange_push(int(n_ranks), int(rank), bitmap or None, int(rows), partial_depth or None,
+                                    partial_uniq or None, P(*recv_bufs), int(n_segs), stream or None))
+
+
+def exchange_reduce(n_ranks, rank, recv_buf, final_depths, final_uniqs, n_segs, stream=0, multicast_base=0,
+                    off_final_depth=0, off_final_uniq=0):
+    """Kernel R (see fgfa_exchange_reduce): add the slots of this rank's slice, store the result to every rank."""
+    P = C.c_void_p * n_ranks
+    _check(lib().fgfa_exchange_reduce(int(n_ranks), int(rank), recv_buf, P(*final_depths), P(*final_uniqs), int(n_segs),
+                                      multicast_base or None, int(off_final_depth), int(off_final_uniq), stream or None))
+
+
 def lpt_partition_c(span_start, span_end, n_parts: int) -> np.ndarray:
     """fgfa_lpt_partition: part index of every path (the C++ partition the multi-GPU ABI uses)."""
     s, e = _u32(span_start), _u32(span_end)
@@ -605,7 +629,10 @@ class DepthPlan:
 
     @staticmethod
     def _ptr(t) -> Optional[int]:
-        return None if t is None else int(t.data_ptr())
+        """Device pointer of a tensor-like (``data_ptr()``), or a raw integer address."""
+        if t is None:
+            return None
+        return int(t) if isinstance(t, int) else int(t.data_ptr())
 
     def run(self, d_steps, d_depth, d_uniq=None, stream: int = 0) -> None:
         """Enqueue memset + kernel A (+ kernel B) on ``stream``; asynchronous."""

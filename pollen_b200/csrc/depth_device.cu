@@ -652,6 +652,79 @@ int fgfa_exchange_uniq_depth(int n_ranks, int rank, const void* const* bitmaps, 
     return FGFA_OK;
 }
 
+static uint32_t exchange_per(int n_ranks, uint32_t n_words) {       // bitmap words per slice: whole 128-byte lines
+    return ((n_words + n_ranks - 1) / n_ranks + 31) & ~31u;
+}
+
+size_t fgfa_exchange_recv_bytes(int n_ranks, uint32_t n_segs) {
+    if (n_ranks < 1) return 0;
+    const uint32_t n_words = (n_segs + 31) / 32;
+    return (size_t)fgfa::push_slot_bytes(std::max(exchange_per(n_ranks, n_words), 32u)) * (size_t)n_ranks;
+}
+
+int fgfa_exchange_push(int n_ranks, int rank, void* bitmap, uint32_t rows, const void* partial_depth,
+                       const void* partial_uniq_u8, void* const* recv_bufs, uint32_t n_segs, void* cuda_stream) {
+    if (n_ranks < 1 || n_ranks > fgfa::kMaxRanks || rank < 0 || rank >= n_ranks || !recv_bufs ||
+        (!partial_uniq_u8 && rows && !bitmap) || (n_segs && !partial_depth) || ((uintptr_t)partial_uniq_u8 & 15u))
+        return fail(FGFA_ERR_INVALID_ARG, "bad exchange arguments");
+    if (rows > 255) return fail(FGFA_ERR_INVALID_ARG, "the fused exchange carries u8 uniq counters (<= 255 paths)");
+    const uint32_t n_words = (n_segs + 31) / 32;
+    if (n_words == 0) return FGFA_OK;
+    fgfa::PushParams P{};
+    P.bitmap = static_cast<uint32_t*>(bitmap);
+    P.partial_depth = static_cast<const uint32_t*>(partial_depth);
+    P.partial_uniq = static_cast<const uint8_t*>(partial_uniq_u8);
+    for (int q = 0; q < n_ranks; ++q) {
+        if (!recv_bufs[q] || ((uintptr_t)recv_bufs[q] & 15u)) return fail(FGFA_ERR_INVALID_ARG, "receive buffers must be 16-byte aligned");
+        P.recv[q] = static_cast<uint8_t*>(recv_bufs[q]);
+    }
+    P.n_ranks = n_ranks;
+    P.rank = rank;
+    P.n_rows = rows;
+    P.words_per_row = (n_words + 31) & ~31u;
+    P.n_words = n_words;
+    P.n_segs = n_segs;
+    P.per = std::max(exchange_per(n_ranks, n_words), 32u);
+    P.uniq_blocks = (n_words + fgfa::kXThreads - 1) / fgfa::kXThreads;
+    const uint32_t depth_blocks = (n_words * 8 + fgfa::kXThreads - 1) / fgfa::kXThreads;
+    fgfa::k_push_partials<<<P.uniq_blocks + depth_blocks, fgfa::kXThreads, 0, (cudaStream_t)cuda_stream>>>(P);
+    CU(cudaGetLastError());
+    return FGFA_OK;
+}
+
+int fgfa_exchange_reduce(int n_ranks, int rank, const void* recv_buf, void* const* final_depths,
+                         void* const* final_uniqs, uint32_t n_segs, void* multicast_base,
+                         uint64_t off_final_depth, uint64_t off_final_uniq, void* cuda_stream) {
+    if (n_ranks < 1 || n_ranks > fgfa::kMaxRanks || rank < 0 || rank >= n_ranks || !recv_buf || !final_depths || !final_uniqs)
+        return fail(FGFA_ERR_INVALID_ARG, "bad exchange arguments");
+    if (multicast_base && ((off_final_depth | off_final_uniq) & 15u))
+        return fail(FGFA_ERR_INVALID_ARG, "multicast regions must be 16-byte aligned");
+    const uint32_t n_words = (n_segs + 31) / 32;
+    if (n_words == 0) return FGFA_OK;
+    fgfa::ReduceParams R{};
+    R.recv = static_cast<const uint8_t*>(recv_buf);
+    for (int q = 0; q < n_ranks; ++q) {
+        R.final_depth[q] = static_cast<uint32_t*>(final_depths[q]);
+        R.final_uniq[q] = static_cast<uint8_t*>(final_uniqs[q]);
+    }
+    R.n_ranks = n_ranks;
+    R.rank = rank;
+    R.n_words = n_words;
+    R.n_segs = n_segs;
+    R.per = std::max(exchange_per(n_ranks, n_words), 32u);
+    R.mc_base = static_cast<uint8_t*>(multicast_base);
+    R.off_final_depth = off_final_depth;
+    R.off_final_uniq = off_final_uniq;
+    const uint32_t w_lo = std::min<uint64_t>((uint64_t)R.per * rank, n_words), w_hi = std::min<uint64_t>((uint64_t)w_lo + R.per, n_words);
+    if (w_hi > w_lo) {
+        const uint64_t slice_segs = (uint64_t)(w_hi - w_lo) * 32;
+        const uint64_t threads = slice_segs / 4 + slice_segs / 16;
+        fgfa::k_reduce_slices<<<(uint32_t)((threads + fgfa::kXThreads - 1) / fgfa::kXThreads), fgfa::kXThreads, 0, (cudaStream_t)cuda_stream>>>(R);
+        CU(cudaGetLastError());
+    }
+    return FGFA_OK;
+}
+
 int fgfa_depth_plan_set_engine(fgfa_depth_plan_t* pl, int engine) {
     if (!pl) return fail(FGFA_ERR_INVALID_ARG, "null plan");
     if (!pl->own_bitmap && engine != 0) return fail(FGFA_ERR_INVALID_ARG, "a plan with an external bitmap runs the stream engine");

@@ -778,4 +778,167 @@ __global__ void __launch_bounds__(kXThreads) k_uniq_exchange(ExchangeParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// kernels P + R: the multi-GPU exchange as PUSH + local reduce (the shipped fused form for N > 2).
+//
+// Kernel X above PULLS: a rank reads its slice of every peer's partial depth and bitmap rows over NVLink.  Reads
+// are round trips; X sustains ~450-510 GB/s of ingress per GPU (profiles/r2_x_nvlink_n8.csv) and the result
+// slices it multicasts afterwards arrive on the same ingress.  Here the first half of the traffic travels as
+// posted stores instead, and the bitmaps never leave their GPU:
+//   kernel P (k_push_partials)  every rank popcounts ITS OWN rows over the WHOLE segment axis (the bit-sliced
+//        counters of kernel B; <= 255 paths, so u8 per segment) and clears them, and copies its partial depth;
+//        each 32-segment word goes straight into slot `rank` of its OWNER's receive buffer -- a peer store for
+//        (N-1)/N of the words.  Out: (N-1)/N x 5 bytes per segment, nothing in.
+//   [inter-rank barrier]
+//   kernel R (k_reduce_slices)  the owner adds the N slots of its slice (local loads only) and stores the final
+//        depth (u32) and uniq (u8) slice to every rank: one multimem.st through the NVSwitch when the buffers
+//        have a multicast mapping, N peer stores otherwise.
+//   [inter-rank barrier]
+// The segment axis is cut into N slices of `per` bitmap words (per = a multiple of 32, i.e. whole 128-byte
+// lines); receive slot s of a rank = { u32 depth[per * 32], u8 uniq[per * 32] } written by rank s.
+// ---------------------------------------------------------------------------
+struct PushParams {
+    uint32_t* __restrict__ bitmap;              // this rank's seen rows [n_rows][words_per_row]; cleared
+    const uint32_t* __restrict__ partial_depth; // this rank's partial depth [n_segs]
+    const uint8_t* __restrict__ partial_uniq;   // or nullptr: this rank's u8 uniq counts, already popcounted (window
+                                                // engine + kernel B2), readable up to a multiple of 32 bytes
+    uint8_t* recv[kMaxRanks];                   // every rank's receive buffer (peer pointers)
+    int n_ranks, rank;
+    uint32_t n_rows, words_per_row;
+    uint32_t n_words, n_segs;
+    uint32_t per;                               // bitmap words per slice
+    uint32_t uniq_blocks;                       // blocks [0, uniq_blocks) popcount, the rest copy depth
+};
+struct ReduceParams {
+    const uint8_t* __restrict__ recv;           // this rank's receive buffer (local)
+    uint32_t* final_depth[kMaxRanks];
+    uint8_t* final_uniq[kMaxRanks];
+    int n_ranks, rank;
+    uint32_t n_words, n_segs, per;
+    uint8_t* mc_base;                           // multicast mapping holding final depth / uniq at the offsets below, or nullptr
+    uint64_t off_final_depth, off_final_uniq;
+};
+__host__ __device__ inline uint64_t push_slot_bytes(uint32_t per) { return (uint64_t)per * 160u; }   // 32 x (4 + 1) bytes per word
+
+__device__ __forceinline__ void st_peer_v4(void* p, uint4 v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(kXThreads) k_push_partials(PushParams P) {
+    if (blockIdx.x < P.uniq_blocks) {
+        // ---- role 1: u8 counts of this rank's rows for one bitmap word, to the word's owner ----
+        const uint32_t w = blockIdx.x * kXThreads + threadIdx.x;
+        if (w >= P.n_words) return;
+        const uint32_t owner = w / P.per, lw = w - owner * P.per;
+        uint8_t* dst = P.recv[owner] + push_slot_bytes(P.per) * P.rank + (size_t)P.per * 128u + (size_t)lw * 32u;
+        if (P.partial_uniq) {                   // the counts exist already: forward the word's 32 bytes
+            const uint4* src = reinterpret_cast<const uint4*>(P.partial_uniq + (size_t)w * 32u);
+            st_peer_v4(dst, src[0]);
+            st_peer_v4(dst + 16, src[1]);
+            return;
+        }
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+        uint32_t* col = P.bitmap + w;
+        for (uint32_t r0 = 0; r0 < P.n_rows; r0 += kXRowsInFlight) {
+            uint32_t x[kXRowsInFlight];
+#pragma unroll
+            for (int k = 0; k < kXRowsInFlight; ++k)
+                x[k] = (r0 + k < P.n_rows) ? col[(size_t)(r0 + k) * P.words_per_row] : 0u;
+#pragma unroll
+            for (int k = 0; k < kXRowsInFlight; ++k) {
+                uint32_t v = x[k], t;
+                if (v) col[(size_t)(r0 + k) * P.words_per_row] = 0u;      // zero bitmap for the next run
+                t = c0 & v; c0 ^= v; v = t;
+                t = c1 & v; c1 ^= v; v = t;
+                t = c2 & v; c2 ^= v; v = t;
+                t = c3 & v; c3 ^= v; v = t;
+                t = c4 & v; c4 ^= v; v = t;
+                t = c5 & v; c5 ^= v; v = t;
+                t = c6 & v; c6 ^= v; v = t;
+                c7 ^= v;
+            }
+        }
+        uint32_t packed[8];                     // 32 u8 counts, segment 32w + j in byte j
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t cnt = ((c0 >> j) & 1u) | (((c1 >> j) & 1u) << 1) | (((c2 >> j) & 1u) << 2) |
+                                 (((c3 >> j) & 1u) << 3) | (((c4 >> j) & 1u) << 4) | (((c5 >> j) & 1u) << 5) |
+                                 (((c6 >> j) & 1u) << 6) | (((c7 >> j) & 1u) << 7);
+            if ((j & 3) == 0) packed[j >> 2] = cnt; else packed[j >> 2] |= cnt << (8 * (j & 3));
+        }
+        st_peer_v4(dst, make_uint4(packed[0], packed[1], packed[2], packed[3]));
+        st_peer_v4(dst + 16, make_uint4(packed[4], packed[5], packed[6], packed[7]));
+    } else {
+        // ---- role 2: partial depth, four segments per thread, to the owner of their word ----
+        const uint64_t seg = ((uint64_t)(blockIdx.x - P.uniq_blocks) * kXThreads + threadIdx.x) * 4;
+        if (seg >= ((uint64_t)P.n_words << 5)) return;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (seg + 4 <= P.n_segs) {
+            v = *reinterpret_cast<const uint4*>(P.partial_depth + seg);
+        } else if (seg < P.n_segs) {
+            v.x = P.partial_depth[seg];
+            if (seg + 1 < P.n_segs) v.y = P.partial_depth[seg + 1];
+            if (seg + 2 < P.n_segs) v.z = P.partial_depth[seg + 2];
+        }
+        const uint32_t w = (uint32_t)(seg >> 5), owner = w / P.per;
+        const uint64_t lseg = seg - (uint64_t)owner * P.per * 32u;
+        st_peer_v4(P.recv[owner] + push_slot_bytes(P.per) * P.rank + lseg * 4u, v);
+    }
+}
+
+__global__ void __launch_bounds__(kXThreads) k_reduce_slices(ReduceParams P) {
+    const uint32_t w_lo = min(P.per * (uint32_t)P.rank, P.n_words), w_hi = min(w_lo + P.per, P.n_words);
+    const uint64_t slice_segs = (uint64_t)(w_hi - w_lo) << 5;          // including the padding of the last word
+    const uint64_t s_base = (uint64_t)w_lo << 5;
+    const uint64_t depth_threads = slice_segs / 4;                     // 4 segments (16 bytes of u32) per thread
+    const uint64_t t = (uint64_t)blockIdx.x * kXThreads + threadIdx.x;
+    if (t < depth_threads) {
+        const uint64_t lseg = t * 4, seg = s_base + lseg;
+        uint4 d = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < kMaxRanks; ++q)
+            if (q < P.n_ranks) {
+                const uint4 x = *reinterpret_cast<const uint4*>(P.recv + push_slot_bytes(P.per) * q + lseg * 4u);
+                d.x += x.x; d.y += x.y; d.z += x.z; d.w += x.w;
+            }
+        if (seg + 4 <= P.n_segs) {
+            if (P.mc_base) {
+                mc_st_v4(P.mc_base + P.off_final_depth + seg * 4, d);
+            } else {
+#pragma unroll
+                for (int q = 0; q < kMaxRanks; ++q)
+                    if (q < P.n_ranks) st_peer_v4(P.final_depth[q] + seg, d);
+            }
+        } else {
+            const uint32_t vals[4] = {d.x, d.y, d.z, d.w};
+            for (uint32_t k = 0; k < 4 && seg + k < P.n_segs; ++k)
+                for (int q = 0; q < P.n_ranks; ++q) P.final_depth[q][seg + k] = vals[k];
+        }
+    } else {
+        // ---- uniq: 16 segments (16 bytes of u8) per thread; packed bytes never carry (<= 255 paths) ----
+        const uint64_t lseg = (t - depth_threads) * 16, seg = s_base + lseg;
+        if (lseg >= slice_segs) return;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < kMaxRanks; ++q)
+            if (q < P.n_ranks) {
+                const uint4 x = *reinterpret_cast<const uint4*>(P.recv + push_slot_bytes(P.per) * q + (size_t)P.per * 128u + lseg);
+                u.x += x.x; u.y += x.y; u.z += x.z; u.w += x.w;
+            }
+        if (seg + 16 <= P.n_segs) {
+            if (P.mc_base) {
+                mc_st_v4(P.mc_base + P.off_final_uniq + seg, u);
+            } else {
+#pragma unroll
+                for (int q = 0; q < kMaxRanks; ++q)
+                    if (q < P.n_ranks) st_peer_v4(P.final_uniq[q] + seg, u);
+            }
+        } else {
+            const uint32_t words[4] = {u.x, u.y, u.z, u.w};
+            for (uint32_t k = 0; k < 16 && seg + k < P.n_segs; ++k)
+                for (int q = 0; q < P.n_ranks; ++q) P.final_uniq[q][seg + k] = (uint8_t)(words[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
 }  // namespace fgfa

@@ -122,7 +122,13 @@ class FusedShardedDepth:
 
     ``rows_per_rank``: number of paths each rank holds (same list on every rank)."""
 
-    def __init__(self, local_start, local_end, n_segs: int, device, rows_per_rank, group=None, use_multicast=True):
+    def __init__(self, local_start, local_end, n_segs: int, device, rows_per_rank, group=None, use_multicast=True,
+                 form: str = "pull", local_engine: str = "stream"):
+        """``form``: "pull" = kernel X (every rank reads its slice of all peers' partials and bitmaps),
+        "push" = kernels P + R (every rank stores its u8 uniq counts and partial depth into the slice owners'
+        receive slots, the owners reduce locally and multicast the result).  ``local_engine`` (push only):
+        "stream" = kernel A + the popcount inside kernel P, "window" = the window engine with u8 uniq counts
+        (kernels S1-S3, W, B2), which kernel P then forwards."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -145,7 +151,13 @@ class FusedShardedDepth:
         self.off_bitmap = al(self.n_segs * 4)
         self.off_final_depth = self.off_bitmap + al(row_bytes * max(1, max(self.rows)))
         self.off_final_uniq = self.off_final_depth + al(self.n_segs * 4)
-        total = self.off_final_uniq + al(self.n_segs)
+        self.off_puniq = self.off_final_uniq + al(self.n_segs)
+        self.off_recv = self.off_puniq + al((self.n_segs + 31) // 32 * 32)
+        assert form in ("pull", "push") and local_engine in ("stream", "window") and (form == "push" or local_engine == "stream")
+        self.form, self.local_engine = form, local_engine
+        from .binding import exchange_recv_bytes
+        self.recv_bytes = exchange_recv_bytes(self.world, self.n_segs) if form == "push" else 0
+        total = self.off_recv + al(self.recv_bytes)
         self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
@@ -156,7 +168,11 @@ class FusedShardedDepth:
         if os.environ.get("FGFA_MULTICAST", "1") == "0":
             use_multicast = False
         self.mc_ptr = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
-        self.plan.use_bitmap(self.ptrs[self.rank] + self.off_bitmap, row_bytes * max(1, self.rows[self.rank]))
+        if local_engine == "window":
+            self.plan.set_uniq_width(1)
+            self.plan.set_engine("window")
+        else:
+            self.plan.use_bitmap(self.ptrs[self.rank] + self.off_bitmap, row_bytes * max(1, self.rows[self.rank]))
         self.bitmap_view = self.buf[self.off_bitmap: self.off_bitmap + row_bytes * max(1, self.rows[self.rank])]
         self.depth = self.buf[self.off_final_depth: self.off_final_depth + 4 * self.n_segs].view(torch.int32)
         self.uniq = self.buf[self.off_final_uniq: self.off_final_uniq + self.n_segs]
@@ -169,6 +185,8 @@ class FusedShardedDepth:
         """NVLink bytes this rank moves per step (in + out)."""
         n, w = self.n_segs, self.world
         slice_segs = -(-n // w)
+        if self.form == "push":                              # partials out as stores, result slices in
+            return (w - 1) * slice_segs * 5 + (w - 1) * slice_segs * 5
         rows_remote = sum(self.rows) - self.rows[self.rank]
         return (w - 1) * slice_segs * 4 + rows_remote * slice_segs // 8 + (w - 1) * slice_segs * 5
 
@@ -180,10 +198,31 @@ class FusedShardedDepth:
         return d, u
 
     def run(self, d_steps, stream=None) -> None:
-        from .binding import exchange_uniq_depth
+        from .binding import exchange_push, exchange_reduce, exchange_uniq_depth
 
         torch = self.torch
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        if self.form == "push":
+            with torch.cuda.stream(st):
+                me = self.ptrs[self.rank]
+                # (every peer finished reducing the previous run before it passed that run's second barrier)
+                if self.local_engine == "window":
+                    self.plan.run(d_steps, me + self.off_partial, me + self.off_puniq, st.cuda_stream)
+                    exchange_push(self.world, self.rank, 0, 0, me + self.off_partial,
+                                  [p + self.off_recv for p in self.ptrs], self.n_segs, st.cuda_stream,
+                                  partial_uniq=me + self.off_puniq)
+                else:
+                    self.plan.run_stream_only(d_steps, me + self.off_partial, st.cuda_stream)
+                    exchange_push(self.world, self.rank, me + self.off_bitmap, self.rows[self.rank], me + self.off_partial,
+                                  [p + self.off_recv for p in self.ptrs], self.n_segs, st.cuda_stream)
+                self.hdl.barrier(channel=0)                  # every rank's slots of my slice have landed
+                exchange_reduce(self.world, self.rank, me + self.off_recv,
+                                [p + self.off_final_depth for p in self.ptrs],
+                                [p + self.off_final_uniq for p in self.ptrs], self.n_segs, st.cuda_stream,
+                                multicast_base=self.mc_ptr, off_final_depth=self.off_final_depth,
+                                off_final_uniq=self.off_final_uniq)
+                self.hdl.barrier(channel=1)                  # every rank's result slices have landed
+            return
         with torch.cuda.stream(st):
             self.plan.run_stream_only(d_steps, self.ptrs[self.rank] + self.off_partial, st.cuda_stream)
             self.hdl.barrier(channel=0)                      # every rank's partials are complete

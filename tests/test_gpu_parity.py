@@ -407,6 +407,74 @@ def test_fused_exchange_kernel_on_one_device(torch_cuda):
             p.close()
 
 
+def test_push_exchange_kernels_on_one_device(torch_cuda):
+    """Kernels P + R (push form of the exchange) with all "ranks" on one GPU: every rank pushes its u8 uniq
+    counts and partial depth into the slice owners' receive slots, then every owner reduces its slice and
+    writes every rank's result buffers.  Sizes with and without a ragged last word / slice."""
+    torch = torch_cuda
+    from pollen_b200.binding import exchange_push, exchange_recv_bytes, exchange_reduce
+    for name, world in (("tinyE", 3), ("B", 4), ("tiny", 7), ("tiny", 1)):
+        cfg = synth.CONFIGS[name]
+        steps, s, e = synth.make_graph(cfg)
+        rc, od, ou = O.depth_with_uniq(steps, s, e, cfg.n_segs)
+        parts = sharding.lpt_partition(e - s, world)
+        st = torch.cuda.current_stream().cuda_stream
+        nbytes = exchange_recv_bytes(world, cfg.n_segs)
+        assert nbytes >= world * 5 * ((cfg.n_segs + world - 1) // world)
+        plans, partial, bitmaps, recv, fin_d, fin_u, keep = [], [], [], [], [], [], []
+        for part in parts:
+            ls_steps, ls, le = synth.make_graph(cfg, path_subset=part)
+            plan = pb.DepthPlan(ls, le, cfg.n_segs, int(le[-1]) if len(le) else 0)
+            bm = torch.zeros(plan.bitmap_row_bytes * max(1, len(part)), dtype=torch.uint8, device="cuda")
+            plan.use_bitmap(bm.data_ptr(), bm.numel())
+            pd = torch.empty(cfg.n_segs, dtype=torch.int32, device="cuda")
+            d_steps = _dev(torch, ls_steps) if len(ls_steps) else torch.zeros(4, dtype=torch.int32, device="cuda")
+            plan.run_stream_only(d_steps, pd.data_ptr(), st)
+            plan.status(st)
+            plans.append(plan); partial.append(pd); bitmaps.append(bm); keep.append(d_steps)
+            recv.append(torch.full((nbytes,), 0x5A, dtype=torch.uint8, device="cuda"))    # every byte read must have been pushed
+            fin_d.append(torch.full((cfg.n_segs,), -1, dtype=torch.int32, device="cuda"))
+            fin_u.append(torch.full((cfg.n_segs,), 255, dtype=torch.uint8, device="cuda"))
+        for _ in range(2):                                  # twice: P leaves the bitmaps clean, so run the stream again
+            for r in range(world):
+                exchange_push(world, r, bitmaps[r].data_ptr(), len(parts[r]), partial[r].data_ptr(),
+                              [t.data_ptr() for t in recv], cfg.n_segs, st)
+            for r in range(world):
+                exchange_reduce(world, r, recv[r].data_ptr(), [t.data_ptr() for t in fin_d],
+                                [t.data_ptr() for t in fin_u], cfg.n_segs, st)
+            torch.cuda.synchronize()
+            for r in range(world):
+                assert (fin_d[r].cpu().numpy().view(np.uint32) == od).all(), (name, r)
+                assert (fin_u[r].cpu().numpy() == ou).all(), (name, r)
+                assert int(bitmaps[r].max()) == 0, (name, r)
+                fin_d[r].fill_(-1); fin_u[r].fill_(255)
+            for r in range(world):
+                plans[r].run_stream_only(keep[r], partial[r].data_ptr(), st)
+        # the same exchange fed with u8 counts that a plan has already popcounted (what the window engine hands over)
+        pu8 = []
+        for r, part in enumerate(parts):
+            ls_steps, ls, le = synth.make_graph(cfg, path_subset=part)
+            q = pb.DepthPlan(ls, le, cfg.n_segs, int(le[-1]) if len(le) else 0)
+            q.set_uniq_width(1)
+            u8 = torch.full(((cfg.n_segs + 31) // 32 * 32,), 0xEE, dtype=torch.uint8, device="cuda")
+            q.run(keep[r], partial[r], u8, st)
+            q.status(st)
+            pu8.append(u8)
+            q.close()
+        for r in range(world):
+            exchange_push(world, r, 0, 0, partial[r].data_ptr(), [t.data_ptr() for t in recv], cfg.n_segs, st,
+                          partial_uniq=pu8[r].data_ptr())
+        for r in range(world):
+            exchange_reduce(world, r, recv[r].data_ptr(), [t.data_ptr() for t in fin_d],
+                            [t.data_ptr() for t in fin_u], cfg.n_segs, st)
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert (fin_d[r].cpu().numpy().view(np.uint32) == od).all(), (name, r)
+            assert (fin_u[r].cpu().numpy() == ou).all(), (name, r)
+        for p in plans:
+            p.close()
+
+
 # ------------------------------------------------------------------- full size ------
 def test_full_size_config_C_vs_oracle_and_properties(torch_cuda):
     """BASELINE.json configs[2]: 5M segments, 90 paths, 400M steps (device-resident)."""

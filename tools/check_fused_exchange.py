@@ -27,15 +27,18 @@ def main():
     d_steps = torch.from_numpy(steps.view(np.int32)).to(dev)
     ref = sharding.ShardedDepth(ls, le, cfg.n_segs, dev, n_paths_global=cfg.n_paths)
     fused = sharding.FusedShardedDepth(ls, le, cfg.n_segs, dev, [len(p) for p in parts])
+    push = sharding.FusedShardedDepth(ls, le, cfg.n_segs, dev, [len(p) for p in parts], form="push")
     st = torch.cuda.current_stream(dev)
     ok = True
     for it in range(3):
         ref.run(d_steps, st); ref.status()
         fused.run(d_steps, st); fused.status()
+        push.run(d_steps, st); push.status()
         torch.cuda.synchronize(dev)
         rd, ru = ref.results()
         fd, fu = fused.results()
-        ok = ok and bool((rd == fd).all() and (ru == fu).all())
+        pd, pu = push.results()
+        ok = ok and bool((rd == fd).all() and (ru == fu).all()) and bool((rd == pd).all() and (ru == pu).all())
     if rank == 0 and cfg.n_steps <= 400_000_000:
         import oracle_lib as O
         full_steps, s, e = synth.make_graph(cfg)
@@ -57,12 +60,14 @@ def main():
         return float(t.item())
     t_ref = timed(lambda: ref.run(d_steps, st))
     t_fused = timed(lambda: fused.run(d_steps, st))
+    t_push = timed(lambda: push.run(d_steps, st))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"config": cfg.name, "n_gpus": world, "parity_fused_vs_nccl_vs_oracle": bool(flag.item()),
                           "engine_nccl_form": ref.plan.engine, "engine_fused_form": fused.plan.engine,
-                          "nccl_step_ms": t_ref, "fused_step_ms": t_fused,
+                          "nccl_step_ms": t_ref, "fused_step_ms": t_fused, "push_step_ms": t_push,
+                          "multicast": bool(push.mc_ptr),
                           "nccl_steps_per_s": cfg.n_steps / (t_ref * 1e-3), "fused_steps_per_s": cfg.n_steps / (t_fused * 1e-3)}))
     dist.destroy_process_group()
 
