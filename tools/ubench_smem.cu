@@ -14,7 +14,7 @@ constexpr int kBytes = 40960;   // + 40 KiB of seen bytes
 
 enum Op { kAtomAdd, kStoreU8, kAtomAddStoreU8, kLoad32, kStore32, kAtomOrBitmap, kAtomAddU16, kAtomAddRet, kStoreU8Cond,
           kAtomAddReg, kAtomOrReg, kAtomOrHeads7, kAtomOrHeads7Distinct, kAtomOrHeads3,
-          kAtomAddOpaque, kAtomOrRet, kAtomAddOrPair, kAtomAddOrPairRet };
+          kAtomAddOpaque, kAtomOrRet, kAtomAddOrPair, kAtomAddOrPairRet, kAtomAdd64, kAtomAddOr64 };
 
 // lane offsets: pattern 0 = consecutive segments, 1 = stride ~2.46 (config C walk), 2 = random in window
 __device__ __forceinline__ uint32_t lane_off(int pattern, uint32_t lane, uint32_t it) {
@@ -94,6 +94,13 @@ __global__ void __launch_bounds__(1024, 1) k_smem(int pattern, int iters, unsign
             asm volatile("atom.shared.or.b32 %0, [%1+81920], %2;" : "=r"(o2) : "r"(a), "r"(1u << (it & 31)) : "memory");
             acc += o1 + o2;
         }
+        if (OP == kAtomAdd64 || OP == kAtomAddOr64) {   // lane l owns the aligned counter pair (2l, 2l+1) of a 64-segment row
+            const uint32_t pair = ((base & ~1u) + 2u * lane) % 20000u & ~1u;
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + pair);
+            const unsigned long long v = (unsigned long long)opaque_one | ((unsigned long long)(it & 1) << 32);
+            asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+            if (OP == kAtomAddOr64) asm volatile("red.shared.or.b64 [%0+81920], %1;" ::"r"(a), "l"(v << 3) : "memory");
+        }
         if (OP == kAtomAddU16) {
             const uint32_t a = (uint32_t)__cvta_generic_to_shared(cnt + (loc >> 1));
             asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(1u << ((loc & 1) << 4)) : "memory");
@@ -153,5 +160,7 @@ int main() {
     run<kAtomOrRet>("ATOMS.OR with return", sms, d_out, d_sink);
     run<kAtomAddOrPair>("ATOMS.ADD RZ + ATOMS.OR RZ", sms, d_out, d_sink);
     run<kAtomAddOrPairRet>("ATOMS.ADD ret + ATOMS.OR ret", sms, d_out, d_sink);
+    run<kAtomAdd64>("ATOMS.ADD.64 lane pairs", sms, d_out, d_sink);
+    run<kAtomAddOr64>("ATOMS.ADD.64 + ATOMS.OR.64", sms, d_out, d_sink);
     return 0;
 }
