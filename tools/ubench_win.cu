@@ -45,6 +45,8 @@ int main(int argc, char** argv) {
     else if (which == "S") cfg = {"S", 5000, 7, 100003ull, 0, 30};
     else if (which == "R") cfg = {"R", 5000000, 90, 400000000ull, 3, 20};
     else if (which == "T") cfg = {"T", 100003, 1000, 3000017ull, 0, 50};   // many short paths
+    else if (which == "C8") cfg = {"C8", 5000000, 11, 50000000ull, 0, 20};   // one rank's share of C at 8 GPUs
+    else if (which == "E8") cfg = {"E8", 5000000, 1, 50000000ull, 1, 0};     // one rank's share of E at 8 GPUs
     else { fprintf(stderr, "unknown cfg\n"); return 2; }
 
     int n_threads = (int)std::thread::hardware_concurrency();
