@@ -175,7 +175,7 @@ int launch_window(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     B.n_batches = batch_hi - batch_lo + 1;
     B.n_keys = B.n_bins * B.n_batches;
     B.n_blocks = (n_sub + fgfa::kBinBlock - 1) / fgfa::kBinBlock;
-    B.max_span = 2 * fgfa::kWinHalo;
+    B.max_span = fgfa::kWinMaxSpan;
     B.keyrank = pl->d_keyrank;
     B.hist = pl->d_hist;
     B.key_total = pl->d_key_total;
@@ -755,7 +755,7 @@ int fgfa_depth_plan_autotune(fgfa_depth_plan_t* pl, const uint32_t* d_steps, voi
     B.path_hi = pl->n_paths;
     B.sub_shift = pl->sub_shift;
     B.n_segs = pl->n_segs;
-    B.max_span = 2 * fgfa::kWinHalo;
+    B.max_span = fgfa::kWinMaxSpan;
     B.ticket = pl->d_ticket;
     CU(cudaMemsetAsync(pl->d_ticket, 0, 8, st));
     fgfa::k_sample_spans<<<(samples + 255) / 256, 256, 0, st>>>(B, samples, n_sub / samples);

@@ -43,7 +43,17 @@
 namespace fgfa {
 
 constexpr int kWinThreads = 1024;                 // kernel W: one CTA per SM
-constexpr uint32_t kWinHalo = 6144;               // segments on each side of the bin
+#ifndef FGFA_WIN_HALO
+#define FGFA_WIN_HALO 6144
+#endif
+constexpr uint32_t kWinHalo = FGFA_WIN_HALO;      // segments on each side of the bin
+// A sub-chunk whose two samples lie further apart than this is not binned ("scattered": every step goes to L2).
+// Measured on config C (profiles/r2_ubench_win_14_span.log): with 2 * halo, 2 % of the sub-chunks were scattered,
+// 3.9 % of all steps went to L2 and their tail cost kernel W 0.1 ms; with 4 * halo 0.19 % of the steps leave
+// shared memory -- the midpoint of the samples is a good window centre even when they are 24 K segments apart,
+// because the window (bin + 2 halos) is 28 K wide.  Larger limits change nothing on C and hurt config E
+// (phase changes of its paths land in windows that hold none of their steps).
+constexpr uint32_t kWinMaxSpan = 4 * kWinHalo;
 // segments per shared-memory window: u32 counter + u32 path mask with uniq, u32 counter alone without
 constexpr uint32_t kWinSegsSeen = 28672, kWinSegsDepth = 57344;
 constexpr uint32_t kBinThreads = 1024;

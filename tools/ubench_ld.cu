@@ -329,7 +329,7 @@ int main(int argc, char** argv) {
     B.n_batches = (cfg.n_paths + 31) / 32;
     B.n_keys = B.n_bins * B.n_batches;
     B.n_blocks = (n_sub + kBinBlock - 1) / kBinBlock;
-    B.max_span = 2 * kWinHalo;
+    B.max_span = kWinMaxSpan;
     uint32_t *d_prefix, *d_keyrank, *d_hist, *d_key_begin, *d_key_total, *d_ticket;
     uint2 *d_entries, *d_entry_tmp;
     CK(cudaMalloc(&d_prefix, (cfg.n_paths + 1) * 4));

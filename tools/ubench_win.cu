@@ -117,7 +117,7 @@ int main(int argc, char** argv) {
         B.n_batches = with_seen ? (cfg.n_paths + 31) / 32 : 1;
         B.n_keys = B.n_bins * B.n_batches;
         B.n_blocks = (n_sub + kBinBlock - 1) / kBinBlock;
-        B.max_span = max_span;
+        B.max_span = getenv("UBENCH_SPAN") ? (uint32_t)atoll(getenv("UBENCH_SPAN")) : max_span;
         if (B.n_keys + 1 > kMaxKeys) { printf("%s: too many keys (%u)\n", name, B.n_keys); return; }
         uint32_t* d_prefix;
         CK(cudaMalloc(&d_prefix, (cfg.n_paths + 1) * 4));
@@ -219,7 +219,7 @@ int main(int argc, char** argv) {
         run_variant(NAME, 8, SEEN ? 1 : 0, [&](uint32_t g, WindowParams& W) {                                 \
             k_window_ring<D, SEEN, false, DBG><<<g, kWinThreads, ring_smem_bytes<D>(SEEN)>>>(W); }, SPAN, ring_win_bin<D>(SEEN)); \
     } while (0)
-    const uint32_t ms_def = 2 * kWinHalo;
+    const uint32_t ms_def = kWinMaxSpan;
     {   // where the steps go (statistics build, not timed meaningfully)
         unsigned long long st[2];
         CK(cudaMemset(d_stats, 0, 16));
@@ -229,6 +229,8 @@ int main(int argc, char** argv) {
     }
     VARIANT("W r8 s2", 8, 2, true, false, 0, ms_def);
     VARIANT_OVL("OVL W r8", 8, true, 0, ms_def);
+    VARIANT_OVL("OVL W r8 span=inf", 8, true, 0, 0xFFFFFFFFu);
+    VARIANT_OVL("OVL W r8 span=2halo", 8, true, 0, 2 * kWinHalo);
     VARIANT_OVL("OVL depth-only r8", 8, false, 0, ms_def);
     VARIANT_OVL("OVL DBG3 loads only", 8, true, 3, ms_def);
     VARIANT_OVL("OVL DBG2 no mask ORs", 8, true, 2, ms_def);
