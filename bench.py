@@ -419,8 +419,13 @@ def main():
     depth_only_ms = timed(lambda: eng.plan.run(d_steps, scratch_depth, None, stream.cuda_stream), args.steps)
     if world > 1 and isinstance(eng, sharding.ShardedDepth):
         allreduce_ms = timed(lambda: sharding.allreduce_counts(eng.out), args.steps)
+    elif world > 1 and getattr(eng, "local_engine", "stream") == "window":
+        # push after the window engine: everything that is not the rank's own S1-S3 + W + B2 (u8 uniq) is exchange
+        scratch_u8 = torch.empty((cfg.n_segs + 31) // 32 * 32, dtype=torch.uint8, device=dev)
+        local_ms = timed(lambda: eng.plan.run(d_steps, scratch_depth, scratch_u8, stream.cuda_stream), args.steps)
+        allreduce_ms = max(0.0, ms_per_step - local_ms)  # kernels P + R + two barriers
     elif world > 1:
-        allreduce_ms = max(0.0, ms_per_step - k_ms)      # barriers + kernel X + bitmap reset
+        allreduce_ms = max(0.0, ms_per_step - k_ms)      # barriers + kernel X (or P + R) + bitmap reset
     else:
         allreduce_ms = 0.0
     eng.run(d_steps, stream)          # leave a valid result behind
