@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
                                          // (3.0 vs 2.5 cycles per warp instruction, tools/ubench_smem.cu)
     unsigned long long n_in = 0, n_out = 0;
 
+    const long long dbg_t0 = DBG == 7 ? clock64() : 0;
     for (uint32_t i = tid; i < (WITH_SEEN ? 2 * kPitch : kPitch); i += kWinThreads) s_cnt[i] = 0u;
     __syncthreads();
 
@@ -532,12 +533,14 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_window_count(WindowParams P)
         const uint32_t b0 = min(n_binned, blockIdx.x * per);
         run_range(b0, min(n_binned, b0 + per), false);
     }
+    if (DBG == 7 && tid == 0) P.stats[2 + 2 * blockIdx.x] = (unsigned long long)(clock64() - dbg_t0);
     {
         const uint32_t n_sc = n_entries - n_binned;
         const uint32_t per = (n_sc + gridDim.x - 1) / gridDim.x;
         const uint32_t s0 = n_binned + min(n_sc, blockIdx.x * per);
         run_range(s0, min(n_entries, s0 + per), true);
     }
+    if (DBG == 7 && tid == 0) P.stats[3 + 2 * blockIdx.x] = (unsigned long long)(clock64() - dbg_t0);
     if (STATS) {
         atomicAdd(P.stats, n_in);
         atomicAdd(P.stats + 1, n_out);

@@ -72,7 +72,7 @@ int main(int argc, char** argv) {
     CK(cudaMemset(d_bitmap, 0, (size_t)cfg.n_paths * wpr * 4));
     CK(cudaMemset(d_err, 0, 4));
     unsigned long long* d_stats;
-    CK(cudaMalloc(&d_stats, 16));
+    CK(cudaMalloc(&d_stats, 16 + 16 * 256));
 
     if (const char* g = getenv("UBENCH_L2_FETCH")) {
         CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)));
@@ -232,6 +232,17 @@ int main(int argc, char** argv) {
     VARIANT_OVL("OVL W r8 span=inf", 8, true, 0, 0xFFFFFFFFu);
     VARIANT_OVL("OVL W r8 span=2halo", 8, true, 0, 2 * kWinHalo);
     VARIANT_OVL("OVL depth-only r8", 8, false, 0, ms_def);
+    if (only && strstr("OVL DBG7 per-CTA cycles", only)) {
+        VARIANT_OVL("OVL DBG7 per-CTA cycles", 8, true, 7, ms_def);
+        std::vector<unsigned long long> st(2 + 2 * 256);
+        CK(cudaMemcpy(st.data(), d_stats, st.size() * 8, cudaMemcpyDeviceToHost));
+        double mn = 1e30, mx = 0, sum = 0, mnb = 1e30, mxb = 0, sumb = 0;
+        for (int b = 0; b < sms; ++b) {
+            const double tb = (double)st[2 + 2 * b], t = (double)st[3 + 2 * b];
+            mn = std::min(mn, t); mx = std::max(mx, t); sum += t; mnb = std::min(mnb, tb); mxb = std::max(mxb, tb); sumb += tb;
+        }
+        printf("  per-CTA cycles: binned range min %.0f avg %.0f max %.0f | whole kernel min %.0f avg %.0f max %.0f\n", mnb, sumb / sms, mxb, mn, sum / sms, mx);
+    }
     VARIANT_OVL("OVL DBG3 loads only", 8, true, 3, ms_def);
     VARIANT_OVL("OVL DBG2 no mask ORs", 8, true, 2, ms_def);
     VARIANT_RING("RING D=1 W", 1, true, 0, ms_def);
