@@ -184,7 +184,7 @@ int launch_window(fgfa_depth_plan* pl, const uint32_t* d_steps_aligned, uint32_t
     B.entries = pl->d_entries;
     B.entry_tmp = pl->d_entry_tmp;
     fgfa::k_bin_rank<<<B.n_blocks, fgfa::kBinThreads, (size_t)(B.n_keys + 1) * 4, st>>>(B);
-    fgfa::k_bin_rowscan<<<B.n_keys + 1, fgfa::kScanThreads, 0, st>>>(B);
+    fgfa::k_bin_keyscan<<<1, fgfa::kScanThreads, 0, st>>>(B);
     fgfa::k_bin_scatter<<<B.n_blocks, fgfa::kBinThreads, 0, st>>>(B);
     CU(cudaGetLastError());
     fgfa::WindowParams W{};
@@ -431,6 +431,7 @@ int fgfa_depth_plan_create(fgfa_depth_plan_t** out, const uint32_t* h_span_start
             CUB_(cudaMalloc(&pl->d_entry_tmp, (size_t)(subs + n_paths + 1) * 8));
             CUB_(cudaMalloc(&pl->d_hist, (size_t)keys * pl->max_blocks * 4));
             CUB_(cudaMalloc(&pl->d_key_total, (size_t)keys * 4));
+            CUB_(cudaMemset(pl->d_key_total, 0, (size_t)keys * 4));      // S1 accumulates into it, S2 clears it again
             CUB_(cudaMalloc(&pl->d_key_begin, (size_t)(keys + 1) * 4));
             CUB_(cudaMalloc(&pl->d_ticket, 8));
             CUB_(cudaMemset(pl->d_ticket, 0, 8));

@@ -13,8 +13,8 @@
 //                              two samples lie further apart than the halo allows go to the
 //                              "scattered" key.  key = bin * n_batches + (path / 32); rank inside
 //                              the block + per-block histogram (key-major).
-//   kernel S2 (k_bin_rowscan)  exclusive scan of every key's row of the histogram matrix; the
-//                              last CTA to finish scans the row totals -> key_begin[].
+//   kernel S2 (k_bin_keyscan)  exclusive scan of the key totals -> key_begin[] (a block's place inside a
+//                              key is the return value of S1's atomicAdd on the key's total).
 //   kernel S3 (k_bin_scatter)  writes the sub-chunk entries {first element, path} in key order.
 //   kernel W  (k_window_count) persistent, one CTA per SM; every CTA takes an EQUAL share of the
 //                              sorted entry list (load balance does not depend on how the steps
@@ -84,8 +84,8 @@ struct BinParams {
     uint32_t n_blocks;                         // CTAs of S1/S3
     uint32_t max_span;                         // |h1 - h0| above this -> scattered
     uint32_t* __restrict__ keyrank;            // [n_sub] key << kRankBits | rank
-    uint32_t* __restrict__ hist;               // [(n_keys + 1) * n_blocks], key-major
-    uint32_t* __restrict__ key_total;          // [n_keys + 1]
+    uint32_t* __restrict__ hist;               // [(n_keys + 1) * n_blocks], key-major: first entry of block b inside key k (set where b holds k)
+    uint32_t* __restrict__ key_total;          // [n_keys + 1], all-zero between pre-passes
     uint32_t* __restrict__ key_begin;          // [n_keys + 2]
     uint32_t* __restrict__ ticket;             // zero between launches
     uint2* __restrict__ entry_tmp;             // [n_sub] the entries in sub-chunk order (S1 -> S3)
@@ -169,7 +169,12 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_rank(BinParams P) {
         if (d < d_hi) P.keyrank[d - d_lo] = (key << kRankBits) | (base + before);
     }
     __syncthreads();
-    for (uint32_t i = tid; i <= P.n_keys; i += kBinThreads) P.hist[(size_t)i * P.n_blocks + blockIdx.x] = s_cnt[i];
+    // this block's place inside every key it holds: one returning atomic per (block, key).  Which block comes first
+    // inside a key is decided by the atomics -- the counting does not care -- and no histogram row has to be scanned.
+    for (uint32_t i = tid; i <= P.n_keys; i += kBinThreads) {
+        const uint32_t c = s_cnt[i];
+        if (c) P.hist[(size_t)i * P.n_blocks + blockIdx.x] = atomicAdd(P.key_total + i, c);
+    }
 }
 
 // Engine probe: `samples` evenly spaced sub-chunks; ticket[0] += sampled, ticket[1] += those S1 would
@@ -193,8 +198,9 @@ __global__ void __launch_bounds__(256) k_sample_spans(BinParams P, uint32_t samp
 }
 
 // ---------------------------------------------------------------------------
-// S2: one CTA per key: exclusive scan of the key's row of hist; the last CTA to finish
-// turns the row totals into key_begin[].
+// S2: one CTA: exclusive scan of the key totals S1 accumulated -> key_begin[]; clears the totals.
+// (Until late in round 2 S1 wrote a keys x blocks histogram and S2 scanned every key's row with one CTA per
+// key: 7.8 us for 919 keys; a block's place inside a key is now the return value of S1's atomicAdd.)
 // ---------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
 
@@ -221,45 +227,20 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return wex + inc - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_bin_rowscan(BinParams P) {
+__global__ void __launch_bounds__(kScanThreads) k_bin_keyscan(BinParams P) {
     __shared__ uint32_t s_warp[kScanThreads / 32];
-    __shared__ uint32_t s_last;
     const uint32_t tid = threadIdx.x;
-    uint32_t* row = P.hist + (size_t)blockIdx.x * P.n_blocks;
     uint32_t carry = 0;
-    for (uint32_t t0 = 0; t0 < P.n_blocks; t0 += kScanThreads * 4) {
-        const uint32_t i = t0 + tid * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i + k < P.n_blocks) ? row[i + k] : 0u;
-        uint32_t total;
-        uint32_t run = carry + block_exclusive_scan(v[0] + v[1] + v[2] + v[3], s_warp, &total);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + k < P.n_blocks) row[i + k] = run;
-            run += v[k];
-        }
-        carry += total;
-    }
-    if (tid == 0) {
-        P.key_total[blockIdx.x] = carry;
-        __threadfence();
-        s_last = atomicAdd(P.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    carry = 0;
     const uint32_t n = P.n_keys + 1;
     for (uint32_t t0 = 0; t0 < n; t0 += kScanThreads) {
         const uint32_t i = t0 + tid;
-        const uint32_t v = i < n ? *(volatile uint32_t*)(P.key_total + i) : 0u;
+        const uint32_t v = i < n ? P.key_total[i] : 0u;
         uint32_t total;
         const uint32_t ex = carry + block_exclusive_scan(v, s_warp, &total);
-        if (i < n) P.key_begin[i] = ex;
+        if (i < n) { P.key_begin[i] = ex; P.key_total[i] = 0u; }       // key_total is all-zero between pre-passes
         carry += total;
     }
-    if (tid == 0) { P.key_begin[n] = carry; *P.ticket = 0u; }
+    if (tid == 0) P.key_begin[n] = carry;
 }
 
 // ---------------------------------------------------------------------------

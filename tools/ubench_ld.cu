@@ -336,6 +336,7 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(d_prefix, prefix.data(), (cfg.n_paths + 1) * 4, cudaMemcpyHostToDevice));
     B.sub_prefix = d_prefix;
     CK(cudaMalloc(&d_key_total, (size_t)(B.n_keys + 1) * 4));
+        CK(cudaMemset(d_key_total, 0, (size_t)(B.n_keys + 1) * 4));
     CK(cudaMalloc(&d_ticket, 4));
     CK(cudaMemset(d_ticket, 0, 4));
     CK(cudaMalloc(&d_keyrank, (size_t)n_sub * 4));
@@ -346,7 +347,7 @@ int main(int argc, char** argv) {
     B.keyrank = d_keyrank; B.hist = d_hist; B.key_begin = d_key_begin; B.entries = d_entries; B.entry_tmp = d_entry_tmp;
     B.key_total = d_key_total; B.ticket = d_ticket;
     k_bin_rank<<<B.n_blocks, kBinThreads, (B.n_keys + 1) * 4>>>(B);
-    k_bin_rowscan<<<B.n_keys + 1, kScanThreads>>>(B);
+    k_bin_keyscan<<<1, kScanThreads>>>(B);
     k_bin_scatter<<<B.n_blocks, kBinThreads>>>(B);
     CK(cudaDeviceSynchronize());
     // drop the entries that touch a span boundary (their 1 KiB may leave the pool): point them at sub-chunk 0

@@ -127,6 +127,7 @@ int main(int argc, char** argv) {
         uint2 *d_entries, *d_entry_tmp;
         const uint64_t pitch = ((uint64_t)cfg.n_segs + 31) & ~31ull;
         CK(cudaMalloc(&d_key_total, (size_t)(B.n_keys + 1) * 4));
+        CK(cudaMemset(d_key_total, 0, (size_t)(B.n_keys + 1) * 4));
         CK(cudaMalloc(&d_ticket, 4));
         CK(cudaMemset(d_ticket, 0, 4));
         CK(cudaMalloc(&d_keyrank, (size_t)std::max(n_sub, 1u) * 4));
@@ -155,7 +156,7 @@ int main(int argc, char** argv) {
             if (n_sub) {
                 k_bin_rank<<<B.n_blocks, kBinThreads, (B.n_keys + 1) * 4>>>(B);
                 CK(cudaEventRecord(ev[5]));
-                k_bin_rowscan<<<B.n_keys + 1, kScanThreads>>>(B);
+                k_bin_keyscan<<<1, kScanThreads>>>(B);
                 CK(cudaEventRecord(ev[6]));
                 k_bin_scatter<<<B.n_blocks, kBinThreads>>>(B);
             }
